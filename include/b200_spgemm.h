@@ -1,0 +1,166 @@
+/* b200_spgemm.h — C-ABI of the B200-native SpGEMM / rMCL hot path.
+ *
+ * Drop-in boundary for ONE path of ankur-maximos/Sparse_Matrix_with_Flops: row-wise Gustavson
+ * CSR x CSR multiplication with flops-based row binning, and the rMCL expansion / inflation /
+ * prune / normalise loop it drives.  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference root).  Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary.  All functions return B200_OK (0) or an error code; the
+ * text of the last error on the calling thread is available from b200_last_error().
+ *
+ * Conventions shared with the reference (nlibs/CSR.h:23-50): 0-based CSR, `int` indices,
+ * `double` values (the reference's QValue built with -DQValue=double -DFDOUBLE), rows need not
+ * be sorted on input, a row must not contain duplicate columns (nlibs/cpu_csr_kernel.h:151-158
+ * relies on this as well).  Host output arrays are malloc() blocks owned by the caller and
+ * released with free(), exactly like CSR::dispose() (nlibs/CSR.h:323-327).
+ *
+ * Output order: every row of C is emitted with ASCENDING column indices (the reference emits
+ * first-touch order and sorts later in CSR::makeOrdered, nlibs/CSR.cc:73-86).
+ */
+#ifndef B200_SPGEMM_H_
+#define B200_SPGEMM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  B200_OK = 0,
+  B200_ERR_BAD_ARG = 1,
+  B200_ERR_CUDA = 2,
+  B200_ERR_HOST_ALLOC = 3,
+  B200_ERR_INT32_OVERFLOW = 4, /* result does not fit the reference's int CSR (CSR.h:38) */
+  B200_ERR_NO_DEVICE = 5,
+  B200_ERR_NCCL = 6,
+  B200_ERR_NOT_INIT = 7
+};
+
+/* Phase timings and counters of the last device call (all times in milliseconds, CUDA events
+ * on the library's stream). */
+typedef struct b200_stats {
+  double ms_total;
+  double ms_flops;     /* flops analysis + scan + binning   (flops_csr_kernel.cc:14-31,61) */
+  double ms_symbolic;  /* nnz(C row) count                  (cpu_csr_kernel.h:234-262)     */
+  double ms_numeric;   /* accumulate + sort (+ rMCL epilogue) (cpu_csr_kernel.h:134-188)   */
+  double ms_other;     /* scans, allocation, compaction                                     */
+  long long products;  /* intermediate products P = sum_i sum_{j in A_i} nnz(B_j)           */
+  long long nnz_out;   /* nnz of the result                                                 */
+  long long nnz_unpruned; /* rMCL only: nnz before pruning (== nnz_out for SpGEMM)          */
+  int launches;        /* kernels of this library launched by the call                      */
+  int bins_rows[16];   /* rows per numeric bin (diagnostic)                                 */
+} b200_stats;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Select CUDA device `device`, create the library stream and memory pool.  Fails loudly with
+ * B200_ERR_NO_DEVICE when no CUDA device is present: there is no CPU fallback. */
+int b200_init(int device);
+int b200_finalize(void);
+const char* b200_last_error(void);
+/* Launch configuration facts, for the harness: SM count and device name. */
+int b200_device_info(int* sm_count, long long* hbm_bytes, char* name, int name_len);
+
+/* ---- host-buffer entry points -------------------------------------------------------- */
+
+/* C = A x B.  Replaces flops_omp_CSR_SpMM (nlibs/flops_csr_kernel.cc:122-142, declared at
+ * nlibs/cpu_csr_kernel.h:95-98) and omp_CSR_SpMM (nlibs/omp_csr_kernel.cc:296-315,
+ * cpu_csr_kernel.h:73-76): same argument meaning; IC/JC/C are malloc()'d here.
+ * Returns B200_ERR_INT32_OVERFLOW if nnz(C) > INT_MAX (use the row-block device API). */
+int b200_spgemm_csr(const int* IA, const int* JA, const double* A, int nnzA,
+                    const int* IB, const int* JB, const double* B, int nnzB,
+                    int** IC, int** JC, double** C, int* nnzC,
+                    int m, int k, int n);
+
+/* One rMCL iteration newMt = prune(inflate(A x B)).  Replaces static_omp_CSR_RMCL_OneStep
+ * (nlibs/static_omp_csr_kernel.cc:208-284, cpu_csr_kernel.h:194-197) and
+ * omp_CSR_RMCL_OneStep (nlibs/omp_csr_kernel.cc:154-198).  `chaos` (may be NULL) receives
+ * max_i (max_j M[i,j] - sum_j M[i,j]^2) of the result (not in the reference). */
+int b200_rmcl_onestep_csr(const int* IA, const int* JA, const double* A, int nnzA,
+                          const int* IB, const int* JB, const double* B, int nnzB,
+                          int** IC, int** JC, double** C, int* nnzC,
+                          int m, int k, int n, double* chaos);
+
+/* The rMCL loop.  Replaces gpuRmclIter (nlibs/gpus/gpu_csr_kernel.cu:281-312, declared at
+ * nlibs/gpus/gpu_csr_kernel.h:5) and mtRmclIter (nlibs/qrmcl.cc:8-84): Mt <- Mgt x Mt with
+ * inflation/prune/normalise, `maxIter` times, or until chaos < eps when eps > 0.  The input
+ * Mt arrays are borrowed; the final Mt is returned in malloc()'d IM/JM/M.  chaos_hist (may be
+ * NULL) must have room for maxIter doubles. */
+int b200_rmcl_iter(int maxIter, double eps,
+                   const int* IG, const int* JG, const double* G, int nnzG,
+                   const int* IT, const int* JT, const double* T, int nnzT,
+                   int** IM, int** JM, double** M, int* nnzM,
+                   int n, int* iters_done, double* chaos_hist);
+
+/* ---- device-resident CSR (replaces CSR::toGpuCSR / toCpuCSR / deviceDispose,
+ *      nlibs/CSR.cc:342-379) ------------------------------------------------------------ */
+
+typedef struct b200_csr* b200_csr_t;
+
+int b200_csr_upload(const int* I, const int* J, const double* V, int rows, int cols, int nnz,
+                    b200_csr_t* out);
+int b200_csr_info(b200_csr_t h, int* rows, int* cols, long long* nnz);
+/* Whole matrix to malloc()'d int CSR; B200_ERR_INT32_OVERFLOW if nnz > INT_MAX. */
+int b200_csr_download(b200_csr_t h, int** I, int** J, double** V, int* nnz);
+/* Rows [row_lo,row_hi) as a malloc()'d int CSR with I[0]=0 (row-block convention of
+ * SURVEY.md §7 hard part 1, for results larger than the reference's int CSR can hold). */
+int b200_csr_download_rows(b200_csr_t h, int row_lo, int row_hi, int** I, int** J, double** V,
+                           int* nnz);
+int b200_csr_free(b200_csr_t h);
+/* Device pointers of a handle (row offsets are 64-bit on the device). */
+int b200_csr_device_ptrs(b200_csr_t h, void** rowptr64, void** colind32, void** values64);
+
+/* C = A x B on the device.  Replaces gpuSpMMWrapper (nlibs/gpus/gpu_csr_kernel.cu:128-172,
+ * gpu_csr_kernel.h:6).  stats may be NULL. */
+int b200_spgemm_device(b200_csr_t A, b200_csr_t B, b200_csr_t* C, b200_stats* stats);
+/* Rows [row_lo,row_hi) of A only: C has row_hi-row_lo rows. (Row-block / multi-GPU shard.) */
+int b200_spgemm_device_rows(b200_csr_t A, b200_csr_t B, int row_lo, int row_hi, b200_csr_t* C,
+                            b200_stats* stats);
+/* One rMCL iteration on the device.  Replaces gpuRmclOneStepWrapper
+ * (nlibs/gpus/gpu_csr_kernel.cu:243-279). */
+int b200_rmcl_step_device(b200_csr_t Mgt, b200_csr_t Mt, b200_csr_t* newMt, double* chaos,
+                          b200_stats* stats);
+int b200_rmcl_step_device_rows(b200_csr_t Mgt, b200_csr_t Mt, int row_lo, int row_hi,
+                               b200_csr_t* newMt, double* chaos, b200_stats* stats);
+
+/* Per-row intermediate-product counts as an exclusive 64-bit prefix sum, prefix[rows] = P.
+ * Replaces dynamic_omp_CSR_flops (nlibs/flops_csr_kernel.cc:14-31).  `prefix` is a host
+ * array of rows+1 long long. */
+int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix);
+/* Equal-flops contiguous row cut points, ends[0..nparts].  Same arithmetic as
+ * arrayEqualPartition64 (nlibs/tools/util.cc:123-135); host-only, no device needed. */
+int b200_equal_partition64(const long long* prefix, int n, int nparts, int* ends);
+
+/* cluster(i) = argmax_j M[i,j], ties -> smallest j (not in the reference).
+ * labels is a host array of `rows` ints; an empty row gets -1. */
+int b200_csr_row_argmax(b200_csr_t h, int* labels);
+/* Concatenate row blocks (device) into one CSR: the all-gather's local assembly step. */
+int b200_csr_concat_rows(const b200_csr_t* blocks, int nblocks, b200_csr_t* out);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) --------------------------------
+ * Not in the reference (single GPU, SURVEY.md §2.1 strategy table).  The 128-byte unique id
+ * is created on rank 0 and shipped to the other ranks by the host program. */
+int b200_comm_unique_id(char id[128]);
+int b200_comm_init(int rank, int nranks, const char id[128]);
+int b200_comm_destroy(void);
+/* Sharded rMCL: every rank holds full Mgt and Mt handles; rank r computes rows
+ * [ends[r],ends[r+1]) (flops-balanced, recomputed every iteration), then the pruned row
+ * blocks are all-gathered and chaos is max-all-reduced.  On return *Mt_io is the full new Mt
+ * on every rank (the old handle is freed). */
+int b200_rmcl_iter_sharded(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* Mt_io,
+                           int* iters_done, double* chaos_hist, double* ms_per_iter);
+
+/* ---- synthetic inputs (harness) ---------------------------------------- *
+ * All return a malloc()'d int CSR with rmclInit semantics (nlibs/qrmcl.cc:126-134): self loop
+ * on every vertex, sorted unique columns, values 1/rowcount.  Release with b200_host_free. */
+int b200_synth_rmat(int scale, int edge_factor, unsigned long long seed, int symmetrise,
+                    int* rows, int** IA, int** JA, double** A, long long* nnz);
+int b200_synth_stencil27(int gx, int gy, int gz, int* rows, int** IA, int** JA, double** A,
+                         long long* nnz);
+int b200_synth_planted(int n, int nblocks, int intra, int inter, unsigned long long seed,
+                       int* rows, int** IA, int** JA, double** A, long long* nnz,
+                       int** labels);
+void b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SPGEMM_H_ */

@@ -1,0 +1,15 @@
+"""B200-native drop-in for the SpGEMM / rMCL hot path of ankur-maximos/Sparse_Matrix_with_Flops.
+
+The product is the C-ABI library ``libb200spgemm.so`` (include/b200_spgemm.h, sources under
+``csrc/``); this package is the host-side mirror of the reference's container / driver
+interface on top of it.  Importing the package does not need a GPU; the first call that
+computes does, and fails loudly without one (there is no CPU fallback).
+"""
+from . import _lib
+from .csr import (CSR, DeviceCSR, RMCL, arrayEqualPartition64, flops_prefix, gpuRmclIter,
+                  gpuRmclOneStep, gpuSpMMWrapper, init, rmclInit, synth_planted, synth_rmat,
+                  synth_stencil27)
+
+__all__ = ["CSR", "DeviceCSR", "RMCL", "arrayEqualPartition64", "flops_prefix", "gpuRmclIter",
+           "gpuRmclOneStep", "gpuSpMMWrapper", "init", "rmclInit", "synth_planted", "synth_rmat",
+           "synth_stencil27", "_lib"]

@@ -1,0 +1,120 @@
+"""ctypes binding of the C-ABI in include/b200_spgemm.h.
+
+This module is plumbing only: it loads ``libb200spgemm.so`` (built in-tree by
+``sparse_matrix_with_flops_b200/csrc/Makefile``) and declares the argument types of every
+entry point.  There is no Python or CPU implementation of the hot path: if the library is
+missing, or if ``b200_init`` finds no CUDA device, the import / call fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200spgemm.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_double_p = C.POINTER(C.c_double)
+c_ll_p = C.POINTER(C.c_longlong)
+csr_t = C.c_void_p
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("ms_total", C.c_double),
+        ("ms_flops", C.c_double),
+        ("ms_symbolic", C.c_double),
+        ("ms_numeric", C.c_double),
+        ("ms_other", C.c_double),
+        ("products", C.c_longlong),
+        ("nnz_out", C.c_longlong),
+        ("nnz_unpruned", C.c_longlong),
+        ("launches", C.c_int),
+        ("bins_rows", C.c_int * 16),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "bins_rows"}
+        d["bins_rows"] = list(self.bins_rows)
+        return d
+
+
+# name -> (restype, argtypes); kept in the order of include/b200_spgemm.h
+SIGNATURES = {
+    "b200_init": (C.c_int, [C.c_int]),
+    "b200_finalize": (C.c_int, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_device_info": (C.c_int, [c_int_p, c_ll_p, C.c_char_p, C.c_int]),
+    "b200_spgemm_csr": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_int_p, c_double_p,
+                                  C.c_int, C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p),
+                                  c_int_p, C.c_int, C.c_int, C.c_int]),
+    "b200_rmcl_onestep_csr": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_int_p,
+                                        c_double_p, C.c_int, C.POINTER(c_int_p), C.POINTER(c_int_p),
+                                        C.POINTER(c_double_p), c_int_p, C.c_int, C.c_int, C.c_int,
+                                        c_double_p]),
+    "b200_rmcl_iter": (C.c_int, [C.c_int, C.c_double, c_int_p, c_int_p, c_double_p, C.c_int, c_int_p,
+                                 c_int_p, c_double_p, C.c_int, C.POINTER(c_int_p), C.POINTER(c_int_p),
+                                 C.POINTER(c_double_p), c_int_p, C.c_int, c_int_p, c_double_p]),
+    "b200_csr_upload": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(csr_t)]),
+    "b200_csr_info": (C.c_int, [csr_t, c_int_p, c_int_p, c_ll_p]),
+    "b200_csr_download": (C.c_int, [csr_t, C.POINTER(c_int_p), C.POINTER(c_int_p),
+                                    C.POINTER(c_double_p), c_int_p]),
+    "b200_csr_download_rows": (C.c_int, [csr_t, C.c_int, C.c_int, C.POINTER(c_int_p),
+                                         C.POINTER(c_int_p), C.POINTER(c_double_p), c_int_p]),
+    "b200_csr_free": (C.c_int, [csr_t]),
+    "b200_csr_device_ptrs": (C.c_int, [csr_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p)]),
+    "b200_spgemm_device": (C.c_int, [csr_t, csr_t, C.POINTER(csr_t), C.POINTER(Stats)]),
+    "b200_spgemm_device_rows": (C.c_int, [csr_t, csr_t, C.c_int, C.c_int, C.POINTER(csr_t),
+                                          C.POINTER(Stats)]),
+    "b200_rmcl_step_device": (C.c_int, [csr_t, csr_t, C.POINTER(csr_t), c_double_p, C.POINTER(Stats)]),
+    "b200_rmcl_step_device_rows": (C.c_int, [csr_t, csr_t, C.c_int, C.c_int, C.POINTER(csr_t),
+                                             c_double_p, C.POINTER(Stats)]),
+    "b200_flops_prefix": (C.c_int, [csr_t, csr_t, c_ll_p]),
+    "b200_equal_partition64": (C.c_int, [c_ll_p, C.c_int, C.c_int, c_int_p]),
+    "b200_csr_row_argmax": (C.c_int, [csr_t, c_int_p]),
+    "b200_csr_concat_rows": (C.c_int, [C.POINTER(csr_t), C.c_int, C.POINTER(csr_t)]),
+    "b200_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "b200_comm_destroy": (C.c_int, []),
+    "b200_rmcl_iter_sharded": (C.c_int, [C.c_int, C.c_double, csr_t, C.POINTER(csr_t), c_int_p,
+                                         c_double_p, c_double_p]),
+    "b200_synth_rmat": (C.c_int, [C.c_int, C.c_int, C.c_ulonglong, C.c_int, c_int_p,
+                                  C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p), c_ll_p]),
+    "b200_synth_stencil27": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(c_int_p),
+                                       C.POINTER(c_int_p), C.POINTER(c_double_p), c_ll_p]),
+    "b200_synth_planted": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, c_int_p,
+                                     C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p),
+                                     c_ll_p, C.POINTER(c_int_p)]),
+    "b200_host_free": (None, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C sparse_matrix_with_flops_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(rc, load().b200_last_error().decode(errors="replace"))

@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference's container / driver interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to the
+reference root) so that tests read like the reference's own:
+
+* ``CSR``            — struct CSR, nlibs/CSR.h:23-379 (rowPtr / colInd / values / rows / cols / nnz)
+* ``CSR.flops_spmm`` / ``omp_spmm`` / ``somp_spmm`` / ``spmm`` — nlibs/CSR.cc:59-71,108-194
+* ``CSR.staticOmpRmclOneStep`` / ``ompRmclOneStep``           — nlibs/CSR.cc:251-276
+* ``CSR.toGpuCSR`` / ``DeviceCSR.toCpuCSR`` / ``deviceDispose`` — nlibs/CSR.cc:342-379
+* ``gpuSpMMWrapper`` / ``gpuRmclIter``                         — nlibs/gpus/gpu_csr_kernel.h:5-6
+* ``rmclInit`` / ``RMCL``                                       — nlibs/qrmcl.cc:126-164
+
+Everything computes on the GPU through the C-ABI (``_lib``); nothing here is a CPU
+implementation.  Output rows have ascending columns (the reference sorts later with
+``makeOrdered``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Stats, c_double_p, c_int_p, check, csr_t
+
+_inited = {"device": None}
+
+
+def init(device=0):
+    """b200_init: select the CUDA device. Raises B200Error when there is no GPU."""
+    lib = _lib.load()
+    check(lib.b200_init(int(device)))
+    _inited["device"] = int(device)
+
+
+def _ensure_init():
+    if _inited["device"] is None:
+        init(0)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _take(ptr, count, dtype):
+    """Copy a malloc()'d result block into numpy and free() it (CSR::dispose semantics)."""
+    lib = _lib.load()
+    if count > 0:
+        out = np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+    else:
+        out = np.zeros(0, dtype=dtype)
+    lib.b200_host_free(C.cast(ptr, C.c_void_p))
+    return out
+
+
+class CSR:
+    """Host CSR with the reference's field names (nlibs/CSR.h:23-50)."""
+
+    def __init__(self, values, colInd, rowPtr, rows, cols, nnz=None):
+        self.rowPtr = np.ascontiguousarray(rowPtr, dtype=np.int32)
+        self.colInd = np.ascontiguousarray(colInd, dtype=np.int32)
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        self.rows, self.cols = int(rows), int(cols)
+        self.nnz = int(self.rowPtr[self.rows]) if nnz is None else int(nnz)
+        assert self.rowPtr.shape[0] == self.rows + 1
+
+    # ---- SpGEMM: all reference variants compute the same product ----------
+    def _mul(self, B, rmcl=False):
+        assert self.cols == B.rows  # nlibs/CSR.cc:183
+        _ensure_init()
+        lib = _lib.load()
+        IC, JC, Cv = c_int_p(), c_int_p(), c_double_p()
+        nnzC = C.c_int(0)
+        if rmcl:
+            chaos = C.c_double(0.0)
+            check(lib.b200_rmcl_onestep_csr(_ip(self.rowPtr), _ip(self.colInd), _dp(self.values), self.nnz,
+                                            _ip(B.rowPtr), _ip(B.colInd), _dp(B.values), B.nnz,
+                                            C.byref(IC), C.byref(JC), C.byref(Cv), C.byref(nnzC),
+                                            self.rows, self.cols, B.cols, C.byref(chaos)))
+        else:
+            check(lib.b200_spgemm_csr(_ip(self.rowPtr), _ip(self.colInd), _dp(self.values), self.nnz,
+                                      _ip(B.rowPtr), _ip(B.colInd), _dp(B.values), B.nnz,
+                                      C.byref(IC), C.byref(JC), C.byref(Cv), C.byref(nnzC),
+                                      self.rows, self.cols, B.cols))
+        out = CSR(_take(Cv, nnzC.value, np.float64), _take(JC, nnzC.value, np.int32),
+                  _take(IC, self.rows + 1, np.int32), self.rows, B.cols, nnzC.value)
+        if rmcl:
+            out.chaos = chaos.value
+        return out
+
+    def flops_spmm(self, B, stride=512):
+        """CSR::flops_spmm (nlibs/CSR.cc:182-194) — `stride` is accepted and unused."""
+        return self._mul(B)
+
+    omp_spmm = flops_spmm     # nlibs/CSR.cc:122-134
+    somp_spmm = flops_spmm    # nlibs/CSR.cc:108-120
+    spmm = flops_spmm         # nlibs/CSR.cc:59-71
+
+    def staticOmpRmclOneStep(self, B, thread_datas=None, stride=512):
+        """CSR::staticOmpRmclOneStep (nlibs/CSR.cc:265-276): self = Mgt, B = Mt."""
+        return self._mul(B, rmcl=True)
+
+    ompRmclOneStep = staticOmpRmclOneStep  # nlibs/CSR.cc:251-263
+
+    # ---- container helpers --------------------------------------------------------------
+    def deepCopy(self):
+        return CSR(self.values.copy(), self.colInd.copy(), self.rowPtr.copy(), self.rows, self.cols, self.nnz)
+
+    def makeOrdered(self):
+        """CSR::makeOrdered (nlibs/CSR.cc:73-86): sort each row by column (host, numpy)."""
+        if self.nnz:
+            rowid = np.repeat(np.arange(self.rows, dtype=np.int64), np.diff(self.rowPtr))
+            order = np.lexsort((self.colInd, rowid))
+            self.colInd = self.colInd[order]
+            self.values = self.values[order]
+        return self
+
+    def rowCount(self, i):
+        return int(self.rowPtr[i + 1] - self.rowPtr[i])
+
+    def toGpuCSR(self):
+        """CSR::toGpuCSR (nlibs/CSR.cc:342-354)."""
+        _ensure_init()
+        lib = _lib.load()
+        h = csr_t()
+        check(lib.b200_csr_upload(_ip(self.rowPtr), _ip(self.colInd), _dp(self.values), self.rows,
+                                  self.cols, self.nnz, C.byref(h)))
+        return DeviceCSR(h)
+
+    def dispose(self):
+        self.rowPtr = self.colInd = self.values = None
+
+
+class DeviceCSR:
+    """Device-resident CSR handle (the role of the device-pointer CSR of nlibs/CSR.cc:342-379)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def info(self):
+        lib = _lib.load()
+        r, c, z = C.c_int(), C.c_int(), C.c_longlong()
+        check(lib.b200_csr_info(self.handle, C.byref(r), C.byref(c), C.byref(z)))
+        return r.value, c.value, z.value
+
+    rows = property(lambda self: self.info()[0])
+    cols = property(lambda self: self.info()[1])
+    nnz = property(lambda self: self.info()[2])
+
+    def toCpuCSR(self, row_lo=None, row_hi=None):
+        """CSR::toCpuCSR (nlibs/CSR.cc:358-371); optionally only rows [row_lo,row_hi)."""
+        lib = _lib.load()
+        rows, cols, _ = self.info()
+        I, J, V = c_int_p(), c_int_p(), c_double_p()
+        nnz = C.c_int(0)
+        if row_lo is None:
+            check(lib.b200_csr_download(self.handle, C.byref(I), C.byref(J), C.byref(V), C.byref(nnz)))
+            m = rows
+        else:
+            check(lib.b200_csr_download_rows(self.handle, row_lo, row_hi, C.byref(I), C.byref(J),
+                                             C.byref(V), C.byref(nnz)))
+            m = row_hi - row_lo
+        return CSR(_take(V, nnz.value, np.float64), _take(J, nnz.value, np.int32),
+                   _take(I, m + 1, np.int32), m, cols, nnz.value)
+
+    def deviceDispose(self):
+        """CSR::deviceDispose (nlibs/CSR.cc:374-378)."""
+        if self.handle:
+            _lib.load().b200_csr_free(self.handle)
+            self.handle = None
+
+    def row_argmax(self):
+        lib = _lib.load()
+        lab = np.empty(self.rows, dtype=np.int32)
+        check(lib.b200_csr_row_argmax(self.handle, _ip(lab)))
+        return lab
+
+
+def gpuSpMMWrapper(dA, dB, row_lo=None, row_hi=None, want_stats=False):
+    """gpuSpMMWrapper (nlibs/gpus/gpu_csr_kernel.cu:128-172): device in, device out."""
+    lib = _lib.load()
+    h = csr_t()
+    st = Stats()
+    if row_lo is None:
+        check(lib.b200_spgemm_device(dA.handle, dB.handle, C.byref(h), C.byref(st)))
+    else:
+        check(lib.b200_spgemm_device_rows(dA.handle, dB.handle, row_lo, row_hi, C.byref(h), C.byref(st)))
+    out = DeviceCSR(h)
+    return (out, st.as_dict()) if want_stats else out
+
+
+def gpuRmclOneStep(dMgt, dMt, row_lo=None, row_hi=None, want_stats=False):
+    """gpuRmclOneStepWrapper (nlibs/gpus/gpu_csr_kernel.cu:243-279). Returns (newMt, chaos)."""
+    lib = _lib.load()
+    h = csr_t()
+    st = Stats()
+    chaos = C.c_double(0.0)
+    if row_lo is None:
+        check(lib.b200_rmcl_step_device(dMgt.handle, dMt.handle, C.byref(h), C.byref(chaos), C.byref(st)))
+    else:
+        check(lib.b200_rmcl_step_device_rows(dMgt.handle, dMt.handle, row_lo, row_hi, C.byref(h),
+                                             C.byref(chaos), C.byref(st)))
+    out = DeviceCSR(h)
+    return (out, chaos.value, st.as_dict()) if want_stats else (out, chaos.value)
+
+
+def gpuRmclIter(maxIter, Mgt, Mt, eps=0.0):
+    """gpuRmclIter (nlibs/gpus/gpu_csr_kernel.cu:281-312): host Mgt, Mt in; final Mt out.
+
+    Returns (Mt, iters_done, chaos_history)."""
+    _ensure_init()
+    lib = _lib.load()
+    I, J, V = c_int_p(), c_int_p(), c_double_p()
+    nnz, iters = C.c_int(0), C.c_int(0)
+    hist = np.zeros(max(1, maxIter), dtype=np.float64)
+    check(lib.b200_rmcl_iter(int(maxIter), float(eps), _ip(Mgt.rowPtr), _ip(Mgt.colInd), _dp(Mgt.values),
+                             Mgt.nnz, _ip(Mt.rowPtr), _ip(Mt.colInd), _dp(Mt.values), Mt.nnz,
+                             C.byref(I), C.byref(J), C.byref(V), C.byref(nnz), Mgt.rows, C.byref(iters),
+                             _dp(hist)))
+    out = CSR(_take(V, nnz.value, np.float64), _take(J, nnz.value, np.int32),
+              _take(I, Mgt.rows + 1, np.int32), Mgt.rows, Mt.cols, nnz.value)
+    return out, iters.value, hist[:iters.value].copy()
+
+
+def rmclInit(rows_idx, cols_idx, n):
+    """rmclInit (nlibs/qrmcl.cc:126-134) on a duplicate-free edge list: self loops, sorted rows,
+    values 1/rowcount.  Input preparation on the host (numpy); not part of the timed path."""
+    r = np.asarray(rows_idx, dtype=np.int64)
+    c = np.asarray(cols_idx, dtype=np.int64)
+    has = np.zeros(n, dtype=bool)
+    has[r[r == c]] = True
+    missing = np.nonzero(~has)[0]
+    r = np.concatenate([r, missing])
+    c = np.concatenate([c, missing])
+    order = np.lexsort((c, r))
+    r, c = r[order], c[order]
+    rowPtr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rowPtr, r + 1, 1)
+    rowPtr = np.cumsum(rowPtr)
+    cnt = np.diff(rowPtr)
+    vals = np.repeat(1.0 / np.maximum(cnt, 1), cnt)
+    return CSR(vals, c.astype(np.int32), rowPtr.astype(np.int32), n, n)
+
+
+def RMCL(Mt0, maxIters=5, eps=0.0):
+    """RMCL (nlibs/qrmcl.cc:136-164) with RunOptions::GPU semantics, starting from an
+    rmclInit()'ed matrix instead of a file: Mgt = Mt.deepCopy(); loop; return Mt."""
+    Mgt = Mt0.deepCopy()
+    Mt, iters, hist = gpuRmclIter(maxIters, Mgt, Mt0, eps)
+    Mt.iters_done, Mt.chaos_hist = iters, hist
+    return Mt
+
+
+# ---- flops analysis / partition ------------------------------------------------------------
+
+def flops_prefix(dA, dB):
+    """dynamic_omp_CSR_flops (nlibs/flops_csr_kernel.cc:14-31): exclusive prefix, [rows]=P."""
+    lib = _lib.load()
+    out = np.empty(dA.rows + 1, dtype=np.int64)
+    check(lib.b200_flops_prefix(dA.handle, dB.handle, out.ctypes.data_as(_lib.c_ll_p)))
+    return out
+
+
+def arrayEqualPartition64(prefix, nparts):
+    """arrayEqualPartition64 (nlibs/tools/util.cc:123-135)."""
+    lib = _lib.load()
+    prefix = np.ascontiguousarray(prefix, dtype=np.int64)
+    ends = np.empty(nparts + 1, dtype=np.int32)
+    check(lib.b200_equal_partition64(prefix.ctypes.data_as(_lib.c_ll_p), prefix.shape[0] - 1, nparts, _ip(ends)))
+    return ends
+
+
+# ---- synthetic inputs --------------------------------------------------------
+
+def _synth_out(n, I, J, V, nnz):
+    return CSR(_take(V, nnz, np.float64), _take(J, nnz, np.int32), _take(I, n + 1, np.int32), n, n, nnz)
+
+
+def synth_rmat(scale, edge_factor=16, seed=12345, symmetrise=False):
+    lib = _lib.load()
+    n, nnz = C.c_int(), C.c_longlong()
+    I, J, V = c_int_p(), c_int_p(), c_double_p()
+    check(lib.b200_synth_rmat(scale, edge_factor, seed, int(symmetrise), C.byref(n), C.byref(I),
+                              C.byref(J), C.byref(V), C.byref(nnz)))
+    return _synth_out(n.value, I, J, V, nnz.value)
+
+
+def synth_stencil27(gx, gy, gz):
+    lib = _lib.load()
+    n, nnz = C.c_int(), C.c_longlong()
+    I, J, V = c_int_p(), c_int_p(), c_double_p()
+    check(lib.b200_synth_stencil27(gx, gy, gz, C.byref(n), C.byref(I), C.byref(J), C.byref(V), C.byref(nnz)))
+    return _synth_out(n.value, I, J, V, nnz.value)
+
+
+def synth_planted(n, nblocks, intra=16, inter=2, seed=12345, want_labels=False):
+    lib = _lib.load()
+    rows, nnz = C.c_int(), C.c_longlong()
+    I, J, V, L = c_int_p(), c_int_p(), c_double_p(), c_int_p()
+    check(lib.b200_synth_planted(n, nblocks, intra, inter, seed, C.byref(rows), C.byref(I), C.byref(J),
+                                 C.byref(V), C.byref(nnz), C.byref(L) if want_labels else None))
+    out = _synth_out(rows.value, I, J, V, nnz.value)
+    if want_labels:
+        return out, _take(L, n, np.int32)
+    return out

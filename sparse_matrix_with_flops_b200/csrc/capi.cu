@@ -1,0 +1,443 @@
+// capi.cu — the C-ABI (include/b200_spgemm.h): context, device CSR container, host-buffer and
+// device-handle entry points.  No algorithm lives here; see spgemm.cu.
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e),
+           file, line, what);
+  g_err = buf;
+  return B200_ERR_CUDA;
+}
+Ctx& ctx() {
+  static Ctx c;
+  return c;
+}
+
+namespace {
+
+__global__ void k_i32_to_i64(const int* __restrict__ in, int64_t* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+// out[i] = in[lo+i] - in[lo]
+__global__ void k_i64_to_i32_rebased(const int64_t* __restrict__ in, int* __restrict__ out,
+                                     long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)(in[i] - in[0]);
+}
+__global__ void k_rebase_rowptr(const int64_t* __restrict__ in, int64_t* __restrict__ out,
+                                long long n, long long add) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] - in[0] + add;
+}
+// argmax per row, ties -> smallest column; one thread per row (rows of a converged Mt are tiny)
+__global__ void k_row_argmax(const int64_t* __restrict__ rp, const int* __restrict__ col,
+                             const double* __restrict__ val, int m, int* __restrict__ lab) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int best = -1;
+  double bv = 0.0;
+  for (int64_t p = rp[i]; p < rp[i + 1]; ++p) {
+    const double v = val[p];
+    const int c = col[p];
+    if (best < 0 || v > bv || (v == bv && c < best)) { best = c; bv = v; }
+  }
+  lab[i] = best;
+}
+
+int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V, int* nnz) {
+  Ctx& c = ctx();
+  if (lo < 0 || hi > d.rows || lo > hi) { set_error("row range out of bounds"); return B200_ERR_BAD_ARG; }
+  const int m = hi - lo;
+  int64_t ends[2] = {0, 0};
+  B200_CUDA(cudaMemcpyAsync(&ends[0], d.rowptr + lo, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+  B200_CUDA(cudaMemcpyAsync(&ends[1], d.rowptr + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  const int64_t cnt = ends[1] - ends[0];
+  if (cnt > INT_MAX) {
+    set_error("row block holds more than INT_MAX entries; download a smaller block");
+    return B200_ERR_INT32_OVERFLOW;
+  }
+  int* hi32 = (int*)malloc(((size_t)m + 1) * sizeof(int));
+  int* hj = (int*)malloc(((size_t)cnt + 1) * sizeof(int));
+  double* hv = (double*)malloc(((size_t)cnt + 1) * sizeof(double));
+  if (!hi32 || !hj || !hv) { free(hi32); free(hj); free(hv); set_error("host malloc failed"); return B200_ERR_HOST_ALLOC; }
+  int* d32 = nullptr;
+  B200_CUDA(dalloc(&d32, (size_t)m + 1));
+  k_i64_to_i32_rebased<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c.stream>>>(d.rowptr + lo, d32, m + 1);
+  B200_CUDA(cudaMemcpyAsync(hi32, d32, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  if (cnt) {
+    B200_CUDA(cudaMemcpyAsync(hj, d.col + ends[0], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaMemcpyAsync(hv, d.val + ends[0], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  }
+  dfree(d32);
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  *I = hi32; *J = hj; *V = hv; *nnz = (int)cnt;
+  return B200_OK;
+}
+
+int upload(const int* I, const int* J, const double* V, int rows, int cols, int nnz, DevCSR* out) {
+  Ctx& c = ctx();
+  if (rows < 0 || cols < 0 || nnz < 0 || !I || (nnz && (!J || !V))) {
+    set_error("bad CSR arguments");
+    return B200_ERR_BAD_ARG;
+  }
+  DevCSR d;
+  d.rows = rows; d.cols = cols; d.nnz = nnz;
+  int* tmp = nullptr;
+  B200_CUDA(dalloc(&tmp, (size_t)rows + 1));
+  B200_CUDA(dalloc(&d.rowptr, (size_t)rows + 1));
+  B200_CUDA(dalloc(&d.col, (size_t)nnz));
+  B200_CUDA(dalloc(&d.val, (size_t)nnz));
+  B200_CUDA(cudaMemcpyAsync(tmp, I, ((size_t)rows + 1) * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  k_i32_to_i64<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, c.stream>>>(tmp, d.rowptr, rows + 1);
+  if (nnz) {
+    B200_CUDA(cudaMemcpyAsync(d.col, J, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    B200_CUDA(cudaMemcpyAsync(d.val, V, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  }
+  dfree(tmp);
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  *out = d;
+  return B200_OK;
+}
+
+void release(DevCSR& d) {
+  dfree(d.rowptr); dfree(d.col); dfree(d.val);
+  d = DevCSR();
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_init(int device) {
+  Ctx& c = ctx();
+  if (c.ready) {
+    if (c.device == device) return B200_OK;
+    b200_finalize();
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); this library has no CPU fallback");
+    return B200_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return B200_ERR_BAD_ARG; }
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p;
+  B200_CUDA(cudaGetDeviceProperties(&p, device));
+  c.device = device;
+  c.sm_count = p.multiProcessorCount;
+  c.smem_optin = p.sharedMemPerBlockOptin;
+  c.hbm_bytes = p.totalGlobalMem;
+  strncpy(c.name, p.name, sizeof(c.name) - 1);
+  B200_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  for (auto& ev : c.ev) B200_CUDA(cudaEventCreate(&ev));
+  // keep freed blocks in the stream-ordered pool: per-iteration cudaMalloc was a cost centre of
+  // the reference's GPU loop (nlibs/gpus/gpu_csr_kernel.cu:258-259)
+  cudaMemPool_t pool;
+  B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thr = ~0ull;
+  B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  c.ready = true;
+  return B200_OK;
+}
+
+int b200_finalize(void) {
+  Ctx& c = ctx();
+  if (!c.ready) return B200_OK;
+  cudaStreamSynchronize(c.stream);
+  for (auto& ev : c.ev) { cudaEventDestroy(ev); ev = nullptr; }
+  cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+  c.ready = false;
+  return B200_OK;
+}
+
+int b200_device_info(int* sm_count, long long* hbm_bytes, char* name, int name_len) {
+  B200_REQUIRE_INIT();
+  Ctx& c = ctx();
+  if (sm_count) *sm_count = c.sm_count;
+  if (hbm_bytes) *hbm_bytes = (long long)c.hbm_bytes;
+  if (name && name_len > 0) { strncpy(name, c.name, name_len - 1); name[name_len - 1] = 0; }
+  return B200_OK;
+}
+
+// ---- device container ----------------------------------------------------------------------
+
+int b200_csr_upload(const int* I, const int* J, const double* V, int rows, int cols, int nnz,
+                    b200_csr_t* out) {
+  B200_REQUIRE_INIT();
+  if (!out) { set_error("null output handle"); return B200_ERR_BAD_ARG; }
+  b200_csr* h = new b200_csr();
+  int rc = upload(I, J, V, rows, cols, nnz, &h->d);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return B200_OK;
+}
+
+int b200_csr_info(b200_csr_t h, int* rows, int* cols, long long* nnz) {
+  if (!h) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  if (rows) *rows = h->d.rows;
+  if (cols) *cols = h->d.cols;
+  if (nnz) *nnz = h->d.nnz;
+  return B200_OK;
+}
+
+int b200_csr_download(b200_csr_t h, int** I, int** J, double** V, int* nnz) {
+  B200_REQUIRE_INIT();
+  if (!h || !I || !J || !V || !nnz) { set_error("null argument"); return B200_ERR_BAD_ARG; }
+  if (h->d.nnz > INT_MAX) {
+    set_error("nnz exceeds INT_MAX: the reference's int CSR cannot hold it; use b200_csr_download_rows");
+    return B200_ERR_INT32_OVERFLOW;
+  }
+  return download_rows(h->d, 0, h->d.rows, I, J, V, nnz);
+}
+
+int b200_csr_download_rows(b200_csr_t h, int row_lo, int row_hi, int** I, int** J, double** V,
+                           int* nnz) {
+  B200_REQUIRE_INIT();
+  if (!h || !I || !J || !V || !nnz) { set_error("null argument"); return B200_ERR_BAD_ARG; }
+  return download_rows(h->d, row_lo, row_hi, I, J, V, nnz);
+}
+
+int b200_csr_free(b200_csr_t h) {
+  if (!h) return B200_OK;
+  if (ctx().ready) { release(h->d); cudaStreamSynchronize(ctx().stream); }
+  delete h;
+  return B200_OK;
+}
+
+int b200_csr_device_ptrs(b200_csr_t h, void** rowptr64, void** colind32, void** values64) {
+  if (!h) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  if (rowptr64) *rowptr64 = h->d.rowptr;
+  if (colind32) *colind32 = h->d.col;
+  if (values64) *values64 = h->d.val;
+  return B200_OK;
+}
+
+// ---- device entry points -------------------------------------------------------------------
+
+static int check_mul(b200_csr_t A, b200_csr_t B, int lo, int hi) {
+  if (!A || !B) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  if (A->d.cols != B->d.rows) {  // assert(cols == B.rows), nlibs/CSR.cc:183
+    set_error("dimension mismatch: A.cols != B.rows");
+    return B200_ERR_BAD_ARG;
+  }
+  if (lo < 0 || hi > A->d.rows || lo > hi) { set_error("row range out of bounds"); return B200_ERR_BAD_ARG; }
+  return B200_OK;
+}
+
+int b200_spgemm_device_rows(b200_csr_t A, b200_csr_t B, int row_lo, int row_hi, b200_csr_t* C,
+                            b200_stats* stats) {
+  B200_REQUIRE_INIT();
+  int rc = check_mul(A, B, row_lo, row_hi);
+  if (rc) return rc;
+  if (!C) { set_error("null output handle"); return B200_ERR_BAD_ARG; }
+  b200_csr* h = new b200_csr();
+  rc = run_pipeline(A->d, B->d, row_lo, row_hi, MODE_SPGEMM, &h->d, nullptr, stats);
+  if (rc) { release(h->d); delete h; return rc; }
+  *C = h;
+  return B200_OK;
+}
+
+int b200_spgemm_device(b200_csr_t A, b200_csr_t B, b200_csr_t* C, b200_stats* stats) {
+  if (!A) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  return b200_spgemm_device_rows(A, B, 0, A->d.rows, C, stats);
+}
+
+int b200_rmcl_step_device_rows(b200_csr_t Mgt, b200_csr_t Mt, int row_lo, int row_hi,
+                               b200_csr_t* newMt, double* chaos, b200_stats* stats) {
+  B200_REQUIRE_INIT();
+  int rc = check_mul(Mgt, Mt, row_lo, row_hi);
+  if (rc) return rc;
+  if (!newMt) { set_error("null output handle"); return B200_ERR_BAD_ARG; }
+  b200_csr* h = new b200_csr();
+  double ch = 0.0;
+  rc = run_pipeline(Mgt->d, Mt->d, row_lo, row_hi, MODE_RMCL, &h->d, &ch, stats);
+  if (rc) { release(h->d); delete h; return rc; }
+  if (chaos) *chaos = ch;
+  *newMt = h;
+  return B200_OK;
+}
+
+int b200_rmcl_step_device(b200_csr_t Mgt, b200_csr_t Mt, b200_csr_t* newMt, double* chaos,
+                          b200_stats* stats) {
+  if (!Mgt) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  return b200_rmcl_step_device_rows(Mgt, Mt, 0, Mgt->d.rows, newMt, chaos, stats);
+}
+
+int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix) {
+  B200_REQUIRE_INIT();
+  int rc = check_mul(A, B, 0, A ? A->d.rows : 0);
+  if (rc) return rc;
+  Ctx& c = ctx();
+  const int m = A->d.rows;
+  int64_t* d_prefix = nullptr;
+  B200_CUDA(dalloc(&d_prefix, (size_t)m + 1));
+  rc = flops_prefix_device(A->d, B->d, 0, m, d_prefix);
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(prefix, d_prefix, ((size_t)m + 1) * sizeof(long long),
+                            cudaMemcpyDeviceToHost, c.stream));
+  dfree(d_prefix);
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  return B200_OK;
+}
+
+// arrayEqualPartition64 (nlibs/tools/util.cc:123-135); host arithmetic only
+int b200_equal_partition64(const long long* prefix, int n, int nparts, int* ends) {
+  if (!prefix || !ends || n < 0 || nparts < 1) { set_error("bad argument"); return B200_ERR_BAD_ARG; }
+  const long long total = prefix[n];
+  const long long chunk = (total + nparts - 1) / nparts;
+  ends[0] = 0;
+  int now = 0;
+  for (int t = 0; t + 1 < nparts; ++t) {
+    const long long target = std::min((long long)(t + 1) * chunk, total);
+    const long long* up = std::upper_bound(prefix + now, prefix + n + 1, target);
+    int e = std::max((int)(up - prefix - 1), now + 1);
+    e = std::min(e, n);
+    ends[t + 1] = e;
+    now = e;
+  }
+  ends[nparts] = n;
+  return B200_OK;
+}
+
+int b200_csr_row_argmax(b200_csr_t h, int* labels) {
+  B200_REQUIRE_INIT();
+  if (!h || !labels) { set_error("null argument"); return B200_ERR_BAD_ARG; }
+  Ctx& c = ctx();
+  const int m = h->d.rows;
+  int* d_lab = nullptr;
+  B200_CUDA(dalloc(&d_lab, (size_t)m));
+  if (m) k_row_argmax<<<(m + 255) / 256, 256, 0, c.stream>>>(h->d.rowptr, h->d.col, h->d.val, m, d_lab);
+  B200_CUDA(cudaMemcpyAsync(labels, d_lab, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  dfree(d_lab);
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  return B200_OK;
+}
+
+int b200_csr_concat_rows(const b200_csr_t* blocks, int nblocks, b200_csr_t* out) {
+  B200_REQUIRE_INIT();
+  if (!blocks || nblocks < 1 || !out) { set_error("bad argument"); return B200_ERR_BAD_ARG; }
+  Ctx& c = ctx();
+  long long rows = 0, nnz = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    if (!blocks[b] || blocks[b]->d.cols != blocks[0]->d.cols) { set_error("blocks disagree on cols"); return B200_ERR_BAD_ARG; }
+    rows += blocks[b]->d.rows;
+    nnz += blocks[b]->d.nnz;
+  }
+  if (rows > INT_MAX) { set_error("too many rows"); return B200_ERR_INT32_OVERFLOW; }
+  b200_csr* h = new b200_csr();
+  DevCSR& d = h->d;
+  d.rows = (int)rows; d.cols = blocks[0]->d.cols; d.nnz = nnz;
+  B200_CUDA(dalloc(&d.rowptr, (size_t)rows + 1));
+  B200_CUDA(dalloc(&d.col, (size_t)nnz));
+  B200_CUDA(dalloc(&d.val, (size_t)nnz));
+  long long r0 = 0, z0 = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const DevCSR& s = blocks[b]->d;
+    k_rebase_rowptr<<<(unsigned)((s.rows + 1 + 255) / 256), 256, 0, c.stream>>>(s.rowptr, d.rowptr + r0, s.rows + 1, z0);
+    if (s.nnz) {
+      B200_CUDA(cudaMemcpyAsync(d.col + z0, s.col, (size_t)s.nnz * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+      B200_CUDA(cudaMemcpyAsync(d.val + z0, s.val, (size_t)s.nnz * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    }
+    r0 += s.rows;
+    z0 += s.nnz;
+  }
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  B200_CUDA(cudaGetLastError());
+  *out = h;
+  return B200_OK;
+}
+
+// ---- host-buffer entry points ----------------------------------------------------------------
+
+static int host_mul(Mode mode, const int* IA, const int* JA, const double* A, int nnzA,
+                    const int* IB, const int* JB, const double* B, int nnzB, int** IC, int** JC,
+                    double** C, int* nnzC, int m, int k, int n, double* chaos) {
+  B200_REQUIRE_INIT();
+  if (!IC || !JC || !C || !nnzC) { set_error("null output argument"); return B200_ERR_BAD_ARG; }
+  DevCSR dA, dB, dC;
+  int rc = upload(IA, JA, A, m, k, nnzA, &dA);
+  if (rc) return rc;
+  rc = upload(IB, JB, B, k, n, nnzB, &dB);
+  if (rc) { release(dA); return rc; }
+  rc = run_pipeline(dA, dB, 0, m, mode, &dC, chaos, nullptr);
+  if (!rc) {
+    if (dC.nnz > INT_MAX) {
+      set_error("nnz(C) exceeds INT_MAX: use the row-block device API");
+      rc = B200_ERR_INT32_OVERFLOW;
+    } else {
+      rc = download_rows(dC, 0, m, IC, JC, C, nnzC);
+    }
+  }
+  release(dA); release(dB); release(dC);
+  cudaStreamSynchronize(ctx().stream);
+  return rc;
+}
+
+int b200_spgemm_csr(const int* IA, const int* JA, const double* A, int nnzA, const int* IB,
+                    const int* JB, const double* B, int nnzB, int** IC, int** JC, double** C,
+                    int* nnzC, int m, int k, int n) {
+  return host_mul(MODE_SPGEMM, IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, nullptr);
+}
+
+int b200_rmcl_onestep_csr(const int* IA, const int* JA, const double* A, int nnzA, const int* IB,
+                          const int* JB, const double* B, int nnzB, int** IC, int** JC, double** C,
+                          int* nnzC, int m, int k, int n, double* chaos) {
+  double ch = 0.0;
+  int rc = host_mul(MODE_RMCL, IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, &ch);
+  if (!rc && chaos) *chaos = ch;
+  return rc;
+}
+
+int b200_rmcl_iter(int maxIter, double eps, const int* IG, const int* JG, const double* G,
+                   int nnzG, const int* IT, const int* JT, const double* T, int nnzT, int** IM,
+                   int** JM, double** M, int* nnzM, int n, int* iters_done, double* chaos_hist) {
+  B200_REQUIRE_INIT();
+  if (!IM || !JM || !M || !nnzM || maxIter < 0) { set_error("bad argument"); return B200_ERR_BAD_ARG; }
+  DevCSR dG, dT;
+  int rc = upload(IG, JG, G, n, n, nnzG, &dG);
+  if (rc) return rc;
+  rc = upload(IT, JT, T, n, n, nnzT, &dT);
+  if (rc) { release(dG); return rc; }
+  int it = 0;
+  for (; it < maxIter; ++it) {
+    DevCSR dN;
+    double ch = 0.0;
+    rc = run_pipeline(dG, dT, 0, n, MODE_RMCL, &dN, &ch, nullptr);
+    if (rc) { release(dN); break; }
+    release(dT);  // Mt.dispose(); Mt = newMt  (nlibs/qrmcl.cc:72-73)
+    dT = dN;
+    if (chaos_hist) chaos_hist[it] = ch;
+    if (eps > 0 && ch < eps) { ++it; break; }
+  }
+  if (!rc) {
+    if (dT.nnz > INT_MAX) { set_error("nnz exceeds INT_MAX"); rc = B200_ERR_INT32_OVERFLOW; }
+    else rc = download_rows(dT, 0, n, IM, JM, M, nnzM);
+  }
+  if (iters_done) *iters_done = it;
+  release(dG); release(dT);
+  cudaStreamSynchronize(ctx().stream);
+  return rc;
+}
+
+}  // extern "C"

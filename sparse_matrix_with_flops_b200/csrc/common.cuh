@@ -1,0 +1,81 @@
+// common.cuh — shared declarations of the B200 SpGEMM / rMCL library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "b200_spgemm.h"
+
+namespace b200 {
+
+// Device-resident CSR (replaces the device mirror of struct CSR, nlibs/CSR.cc:342-379).
+// Layout in HBM: rowptr int64[rows+1] (64-bit so that nnz(C) > 2^31 fits, SURVEY.md §7 hard
+// part 1), col int32[nnz], val fp64[nnz]; three separate allocations from the stream-ordered
+// pool so row blocks can be viewed without copies.
+struct DevCSR {
+  int64_t* rowptr = nullptr;
+  int* col = nullptr;
+  double* val = nullptr;
+  int rows = 0, cols = 0;
+  int64_t nnz = 0;
+};
+
+}  // namespace b200
+// the opaque handle of include/b200_spgemm.h
+struct b200_csr {
+  b200::DevCSR d;
+};
+namespace b200 {
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  size_t hbm_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  char name[128] = {0};
+};
+Ctx& ctx();
+
+void set_error(const std::string& s);
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define B200_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return b200::fail_cuda(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define B200_REQUIRE_INIT()                                                     \
+  do {                                                                          \
+    if (!b200::ctx().ready) {                                                   \
+      b200::set_error("b200_init() has not been called (no CPU fallback exists)"); \
+      return B200_ERR_NOT_INIT;                                                 \
+    }                                                                           \
+  } while (0)
+
+// stream-ordered allocation helpers
+template <typename T>
+inline cudaError_t dalloc(T** p, size_t count) {
+  if (count == 0) count = 1;
+  return cudaMallocAsync((void**)p, count * sizeof(T), ctx().stream);
+}
+template <typename T>
+inline void dfree(T* p) {
+  if (p) cudaFreeAsync((void*)p, ctx().stream);
+}
+
+// mode of the row pipeline
+enum Mode { MODE_SPGEMM = 0, MODE_RMCL = 1 };
+
+// Core pipeline (spgemm.cu): C = A[row_lo:row_hi) x B, or the fused rMCL step.
+int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode,
+                 DevCSR* C, double* chaos, b200_stats* stats);
+
+// flops prefix on device (spgemm.cu)
+int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,
+                        int64_t* d_prefix /* rows+1 */);
+
+}  // namespace b200

@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/b200_spgemm.h declares, refuses to compute without a GPU, and its host-only pieces
+(partition arithmetic, generators) agree with the checker.  No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(smf):
+    header = open(os.path.join(ROOT, "include", "b200_spgemm.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200_csr_t"}
+    assert len(declared) >= 25
+    lib = smf._lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200_spgemm.h but not exported"
+    assert declared == set(smf._lib.SIGNATURES), declared ^ set(smf._lib.SIGNATURES)
+
+
+def test_no_cpu_fallback(smf):
+    """Without a CUDA device b200_init must fail and compute entry points must refuse."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = smf._lib.load()
+    assert lib.b200_init(0) == 5  # B200_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.b200_last_error()
+    A = smf.synth_rmat(5, 4, 1, True)
+    with pytest.raises(smf._lib.B200Error):
+        A.flops_spmm(A)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under sparse_matrix_with_flops_b200/ may reference oracle/."""
+    pkg = os.path.join(ROOT, "sparse_matrix_with_flops_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in text and "oracle_" not in text and "libref" not in text, f
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 8, 64])
+def test_equal_partition_matches_oracle(smf, parts):
+    rng = np.random.default_rng(parts)
+    for n in (1, 2, 17, 1000):
+        f = rng.integers(0, 50, size=n)
+        f[rng.integers(0, n)] += 5000  # a hub row
+        pre = np.concatenate([[0], np.cumsum(f)]).astype(np.int64)
+        assert np.array_equal(smf.arrayEqualPartition64(pre, parts), ol.o_equal_partition64(pre, parts))
+    pre = np.zeros(11, dtype=np.int64)  # all-empty product
+    assert np.array_equal(smf.arrayEqualPartition64(pre, parts), ol.o_equal_partition64(pre, parts))
+
+
+def _check_rmclinit_semantics(A):
+    assert A.rowPtr[0] == 0 and A.rowPtr[-1] == A.nnz
+    for i in range(A.rows):
+        cols = A.colInd[A.rowPtr[i]:A.rowPtr[i + 1]]
+        assert np.all(np.diff(cols) > 0), "sorted, duplicate-free"
+        assert i in cols, "self loop"
+        assert np.all(A.values[A.rowPtr[i]:A.rowPtr[i + 1]] == 1.0 / len(cols))
+
+
+def test_generators(smf):
+    A = smf.synth_rmat(7, 8, 12345, True)
+    assert A.rows == 128
+    _check_rmclinit_semantics(A)
+    B = smf.synth_rmat(7, 8, 12345, True)
+    assert np.array_equal(A.colInd, B.colInd)  # deterministic
+    dense = np.zeros((128, 128), dtype=bool)
+    dense[np.repeat(np.arange(128), np.diff(A.rowPtr)), A.colInd] = True
+    assert np.array_equal(dense, dense.T), "symmetrised"
+    S = smf.synth_stencil27(4, 3, 5)
+    assert S.rows == 60
+    _check_rmclinit_semantics(S)
+    cnt = np.diff(S.rowPtr)
+    assert cnt.max() == 27 and cnt.min() == 8
+    P, lab = smf.synth_planted(300, 3, 5, 1, 7, want_labels=True)
+    _check_rmclinit_semantics(P)
+    assert list(np.unique(lab)) == [0, 1, 2]
+
+
+def test_rmclinit_host_mirror_matches_oracle(smf, golden):
+    m = smf.rmclInit(golden["t2_edges_r"], golden["t2_edges_c"], 3)
+    assert np.array_equal(m.rowPtr, golden["t2_A_I"]) and np.array_equal(m.colInd, golden["t2_A_J"])
+    assert np.array_equal(m.values, golden["t2_A_V"])

@@ -1,0 +1,225 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the checker
+(oracle/oracle.c, itself pinned to the reference) on the same seeded inputs and against the
+committed golden vectors.  Bar (BASELINE.json north_star): rowPtr exact, per-row sorted colInd
+exact, values within 1e-12 relative; cluster labels exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12  # relative, per entry (north_star)
+
+
+def M_of(c):
+    return ol.from_csr(c)
+
+
+def gpu_spgemm(smf, A, B):
+    """Through the host-buffer entry point b200_spgemm_csr (mirror of CSR::flops_spmm)."""
+    C = A.flops_spmm(B)
+    return M_of(C)
+
+
+def want_spgemm(A, B):
+    return ol.o_make_ordered(ol.o_spgemm(M_of(A), M_of(B)))
+
+
+def random_csr(smf, rows, cols, density, seed, sort=True, empty_rows=0.0):
+    rng = np.random.default_rng(seed)
+    cnt = rng.binomial(cols, density, size=rows)
+    cnt[rng.random(rows) < empty_rows] = 0
+    rowPtr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    colInd = np.empty(rowPtr[-1], dtype=np.int32)
+    for i in range(rows):
+        c = rng.choice(cols, size=cnt[i], replace=False)
+        colInd[rowPtr[i]:rowPtr[i + 1]] = np.sort(c) if sort else c
+    vals = rng.random(rowPtr[-1]) + 0.01
+    return smf.CSR(vals, colInd, rowPtr, rows, cols)
+
+
+GOLDEN = ["t2", "mtx4a", "mtx4b", "rmat8", "stencil543", "planted200"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_spgemm_golden(gpu, golden, name):
+    r, c = golden[name + "_A_shape"]
+    A = gpu.CSR(golden[name + "_A_V"], golden[name + "_A_J"], golden[name + "_A_I"], int(r), int(c))
+    got = gpu_spgemm(gpu, A, A)
+    want = ol.M(golden[name + "_AA_sorted_I"], golden[name + "_AA_sorted_J"], golden[name + "_AA_sorted_V"], int(r), int(c))
+    ol.assert_same(got, want, TOL, name)
+
+
+@pytest.mark.parametrize("name", [g for g in GOLDEN if g != "mtx4b"])
+def test_rmcl_golden(gpu, golden, name):
+    r, c = golden[name + "_A_shape"]
+    A = gpu.CSR(golden[name + "_A_V"], golden[name + "_A_J"], golden[name + "_A_I"], int(r), int(c))
+    step = M_of(A.staticOmpRmclOneStep(A))
+    ol.assert_same(step, ol.M(golden[name + "_step_sorted_I"], golden[name + "_step_sorted_J"],
+                              golden[name + "_step_sorted_V"], int(r), int(c)), TOL, name + " step")
+    Mt, iters, hist = gpu.gpuRmclIter(6, A, A)
+    assert iters == 6
+    ol.assert_same(M_of(Mt), ol.M(golden[name + "_iter6_sorted_I"], golden[name + "_iter6_sorted_J"],
+                                  golden[name + "_iter6_sorted_V"], int(r), int(c)), TOL, name + " 6 iters")
+
+
+SYNTH = [
+    ("rmat10_sym", lambda s: s.synth_rmat(10, 16, 12345, True)),       # hub rows -> bitmap bin
+    ("rmat12_dir", lambda s: s.synth_rmat(12, 16, 12345, False)),
+    ("rmat13_sym_ef4", lambda s: s.synth_rmat(13, 4, 7, True)),
+    ("stencil_9x8x7", lambda s: s.synth_stencil27(9, 8, 7)),           # all rows in warp bins
+    ("stencil_1x1x40", lambda s: s.synth_stencil27(1, 1, 40)),
+    ("planted_3000", lambda s: s.synth_planted(3000, 10, 16, 2, 12345)),
+]
+
+
+@pytest.mark.parametrize("name,make", SYNTH)
+def test_spgemm_synthetic(gpu, name, make):
+    A = make(gpu)
+    got = gpu_spgemm(gpu, A, A)
+    ol.assert_same(got, want_spgemm(A, A), TOL, name)
+
+
+@pytest.mark.parametrize("name,make", SYNTH)
+def test_rmcl_synthetic(gpu, name, make):
+    A = make(gpu)
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+    step = A.staticOmpRmclOneStep(A)
+    ol.assert_same(M_of(step), want1, TOL, name + " one step")
+    assert abs(step.chaos - ol.o_chaos(want1)) <= 1e-12
+    want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 8)
+    ol.o_make_ordered(want)
+    Mt, iters, hist = gpu.gpuRmclIter(8, A, A)
+    assert iters == it_w == 8
+    ol.assert_same(M_of(Mt), want, TOL, name + " 8 iterations")
+    assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
+    # cluster labels: argmax per row, ties -> lowest column, bit-exact
+    d = Mt.toGpuCSR()
+    assert np.array_equal(d.row_argmax(), ol.o_row_argmax(want))
+    d.deviceDispose()
+
+
+def test_small_rows_are_bit_identical(gpu):
+    """Warp-per-row bins reproduce the reference's accumulation order: values bitwise equal."""
+    A = gpu.synth_stencil27(10, 9, 8)
+    got, want = gpu_spgemm(gpu, A, A), want_spgemm(A, A)
+    assert np.array_equal(got.V.view(np.int64), want.V.view(np.int64))
+
+
+def test_rmcl_to_convergence(gpu):
+    A = gpu.synth_planted(2000, 8, 16, 1, 3)
+    want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 40, eps=1e-6)
+    Mt, iters, hist = gpu.gpuRmclIter(40, A, A, eps=1e-6)
+    assert iters == it_w and iters < 40
+    ol.assert_same(M_of(Mt), ol.o_make_ordered(want), TOL, "converged Mt")
+    assert np.array_equal(ol.o_row_argmax(M_of(Mt)), ol.o_row_argmax(want))
+
+
+def test_rectangular_unsorted_and_empty_rows(gpu):
+    A = random_csr(gpu, 300, 200, 0.03, 1, empty_rows=0.2)
+    B = random_csr(gpu, 200, 500, 0.05, 2, sort=False, empty_rows=0.1)
+    ol.assert_same(gpu_spgemm(gpu, A, B), want_spgemm(A, B), TOL, "rect")
+
+
+def test_dense_rows_each_bin(gpu):
+    """Rows sized to land in every symbolic / numeric bin, incl. the hash tables at capacity."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    B = random_csr(gpu, n, n, 0.02, 11)           # ~100 per row
+    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 127, 128, 129, 600, 1500, 3000]
+    rowPtr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    cols = np.concatenate([np.sort(rng.choice(n, size=s, replace=False)) for s in sizes]).astype(np.int32)
+    A = gpu.CSR(rng.random(len(cols)) + 0.1, cols, rowPtr, len(sizes), n)
+    ol.assert_same(gpu_spgemm(gpu, A, B), want_spgemm(A, B), TOL, "bins")
+
+
+def test_exact_capacity_rows(gpu):
+    """nnz(C row) exactly 64 / 256 / 1024 / 1025 (numeric bin boundaries)."""
+    n = 4096
+    targets = [63, 64, 65, 255, 256, 257, 1023, 1024, 1025, 4096]
+    # B = identity; A row i has `t` entries -> C row has exactly t entries
+    B = gpu.CSR(np.ones(n), np.arange(n, dtype=np.int32), np.arange(n + 1, dtype=np.int32), n, n)
+    rng = np.random.default_rng(9)
+    rowPtr = np.concatenate([[0], np.cumsum(targets)]).astype(np.int32)
+    cols = np.concatenate([np.sort(rng.choice(n, size=t, replace=False)) for t in targets]).astype(np.int32)
+    A = gpu.CSR(rng.random(len(cols)) + 0.5, cols, rowPtr, len(targets), n)
+    got = gpu_spgemm(gpu, A, B)
+    ol.assert_same(got, want_spgemm(A, B), TOL, "capacity")
+    assert list(np.diff(got.I)) == targets
+
+
+def test_empty_operands(gpu):
+    Z = gpu.CSR(np.zeros(0), np.zeros(0, dtype=np.int32), np.zeros(6, dtype=np.int32), 5, 5)
+    C = Z.flops_spmm(Z)
+    assert C.nnz == 0 and list(C.rowPtr) == [0] * 6
+    A = gpu.synth_rmat(5, 4, 1, True)
+    C = A.flops_spmm(gpu.CSR(np.zeros(0), np.zeros(0, dtype=np.int32), np.zeros(A.rows + 1, dtype=np.int32), A.rows, 7))
+    assert C.nnz == 0 and C.cols == 7
+
+
+def test_wide_matrix_uses_hbm_bitmap(gpu):
+    """More columns than the shared-memory bitmap holds (n > 1.8M): HBM bitmap variant."""
+    n = 2_500_000
+    rng = np.random.default_rng(3)
+    k = 400
+    # B: k rows, each ~60 columns spread over n
+    cnt = np.full(k, 60)
+    rowPtr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    cols = np.concatenate([np.sort(rng.choice(n, size=60, replace=False)) for _ in range(k)]).astype(np.int32)
+    B = gpu.CSR(rng.random(len(cols)) + 0.1, cols, rowPtr, k, n)
+    # A: 6 rows; two of them reference many B rows (P > 8192 -> bitmap bins)
+    sizes = [3, 350, 40, 400, 0, 200]
+    arp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    acol = np.concatenate([np.sort(rng.choice(k, size=s, replace=False)) for s in sizes]).astype(np.int32)
+    A = gpu.CSR(rng.random(len(acol)) + 0.1, acol, arp, len(sizes), k)
+    ol.assert_same(gpu_spgemm(gpu, A, B), want_spgemm(A, B), TOL, "wide")
+
+
+def test_row_blocks_concatenate_to_the_whole(gpu):
+    """SURVEY.md §7 hard part 1: row-block calls with flops-balanced cut points."""
+    A = gpu.synth_rmat(11, 8, 5, True)
+    dA = A.toGpuCSR()
+    pre = gpu.flops_prefix(dA, dA)
+    assert np.array_equal(pre, ol.o_flops_prefix(M_of(A), M_of(A)))
+    ends = gpu.arrayEqualPartition64(pre, 3)
+    assert np.array_equal(ends, ol.o_equal_partition64(pre, 3))
+    whole = want_spgemm(A, A)
+    for b in range(3):
+        lo, hi = int(ends[b]), int(ends[b + 1])
+        dC = gpu.gpuSpMMWrapper(dA, dA, lo, hi)
+        got = M_of(dC.toCpuCSR())
+        dC.deviceDispose()
+        assert np.array_equal(got.I, whole.I[lo:hi + 1] - whole.I[lo])
+        s, e = whole.I[lo], whole.I[hi]
+        assert np.array_equal(got.J, whole.J[s:e])
+        assert np.all(np.abs(got.V - whole.V[s:e]) <= TOL * np.abs(whole.V[s:e]))
+    dA.deviceDispose()
+
+
+def test_properties_at_scale(gpu):
+    """Size-independent properties on a graph too large for the checker to be quick:
+    (1) every row of an rMCL step sums to 1 and is sorted; (2) SpGEMM row sums obey
+    sum_j C[i,j] = sum_k A[i,k] * rowsum(B[k,:]) (linearity); (3) nnz(C) <= products."""
+    A = gpu.synth_rmat(15, 16, 99, True)
+    dA = A.toGpuCSR()
+    dC, st = gpu.gpuSpMMWrapper(dA, dA, want_stats=True)
+    assert st["nnz_out"] <= st["products"]
+    C = dC.toCpuCSR()
+    dC.deviceDispose()
+    rowid = np.repeat(np.arange(C.rows), np.diff(C.rowPtr))
+    assert np.all(np.diff(C.colInd)[np.diff(rowid) == 0] > 0), "ascending columns"
+    rs_B = np.add.reduceat(A.values, A.rowPtr[:-1])
+    want_rs = np.add.reduceat(A.values * rs_B[A.colInd], A.rowPtr[:-1])
+    got_rs = np.zeros(C.rows)
+    np.add.at(got_rs, rowid, C.values)
+    assert np.allclose(got_rs, want_rs, rtol=1e-12, atol=0)
+    dM, chaos = gpu.gpuRmclOneStep(dA, dA)
+    Mt = dM.toCpuCSR()
+    dM.deviceDispose()
+    dA.deviceDispose()
+    rid = np.repeat(np.arange(Mt.rows), np.diff(Mt.rowPtr))
+    sums = np.zeros(Mt.rows)
+    np.add.at(sums, rid, Mt.values)
+    assert np.allclose(sums, 1.0, rtol=0, atol=1e-12)
+    assert np.all(np.diff(Mt.colInd)[np.diff(rid) == 0] > 0)
+    assert 0.0 <= chaos <= 1.0
