@@ -13,8 +13,14 @@
  * relies on this as well).  Host output arrays are malloc() blocks owned by the caller and
  * released with free(), exactly like CSR::dispose() (nlibs/CSR.h:323-327).
  *
- * Output order: every row of C is emitted with ASCENDING column indices (the reference emits
- * first-touch order and sorts later in CSR::makeOrdered, nlibs/CSR.cc:73-86).
+ * Output order.  SpGEMM: every row of C has ASCENDING column indices (the reference emits
+ * first-touch order and sorts later in CSR::makeOrdered, nlibs/CSR.cc:73-86).  A single rMCL
+ * step (b200_rmcl_onestep_csr, b200_rmcl_step_device*) keeps the REFERENCE's storage order —
+ * first-touch order with pruned entries removed — for every row computed by a hash bin,
+ * because the next iteration's row sums run in that order and only so do the iterates stay
+ * bit-identical to the reference's; rows computed by the large-row (bitmap) bin come out
+ * ascending.  The loops (b200_rmcl_iter, b200_rmcl_iter_sharded) sort the final matrix
+ * (makeOrdered) before returning it; b200_csr_sort_rows does it on demand.
  */
 #ifndef B200_SPGEMM_H_
 #define B200_SPGEMM_H_
@@ -81,7 +87,9 @@ int b200_rmcl_onestep_csr(const int* IA, const int* JA, const double* A, int nnz
 
 /* The rMCL loop.  Replaces gpuRmclIter (nlibs/gpus/gpu_csr_kernel.cu:281-312, declared at
  * nlibs/gpus/gpu_csr_kernel.h:5) and mtRmclIter (nlibs/qrmcl.cc:8-84): Mt <- Mgt x Mt with
- * inflation/prune/normalise, `maxIter` times, or until chaos < eps when eps > 0.  The input
+ * inflation/prune/normalise, `maxIter` times; with eps > 0 it also stops after the first iteration whose chaos is
+ * < eps or moved by less than eps since the previous iteration (the reference's
+ * loop is fixed-count; oracle/oracle.c states the same rule for the checker).  The input
  * Mt arrays are borrowed; the final Mt is returned in malloc()'d IM/JM/M.  chaos_hist (may be
  * NULL) must have room for maxIter doubles. */
 int b200_rmcl_iter(int maxIter, double eps,
@@ -105,6 +113,8 @@ int b200_csr_download(b200_csr_t h, int** I, int** J, double** V, int* nnz);
 int b200_csr_download_rows(b200_csr_t h, int row_lo, int row_hi, int** I, int** J, double** V,
                            int* nnz);
 int b200_csr_free(b200_csr_t h);
+/* CSR::makeOrdered (nlibs/CSR.cc:73-86) on the device: sort every row by column, in place. */
+int b200_csr_sort_rows(b200_csr_t h);
 /* Device pointers of a handle (row offsets are 64-bit on the device). */
 int b200_csr_device_ptrs(b200_csr_t h, void** rowptr64, void** colind32, void** values64);
 

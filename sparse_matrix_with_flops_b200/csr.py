@@ -165,6 +165,11 @@ class DeviceCSR:
         return CSR(_take(V, nnz.value, np.float64), _take(J, nnz.value, np.int32),
                    _take(I, m + 1, np.int32), m, cols, nnz.value)
 
+    def makeOrdered(self):
+        """CSR::makeOrdered (nlibs/CSR.cc:73-86) on the device."""
+        check(_lib.load().b200_csr_sort_rows(self.handle))
+        return self
+
     def deviceDispose(self):
         """CSR::deviceDispose (nlibs/CSR.cc:374-378)."""
         if self.handle:

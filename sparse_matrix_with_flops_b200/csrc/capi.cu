@@ -225,6 +225,12 @@ int b200_csr_free(b200_csr_t h) {
   return B200_OK;
 }
 
+int b200_csr_sort_rows(b200_csr_t h) {
+  B200_REQUIRE_INIT();
+  if (!h) { set_error("null handle"); return B200_ERR_BAD_ARG; }
+  return sort_rows_device(&h->d);
+}
+
 int b200_csr_device_ptrs(b200_csr_t h, void** rowptr64, void** colind32, void** values64) {
   if (!h) { set_error("null handle"); return B200_ERR_BAD_ARG; }
   if (rowptr64) *rowptr64 = h->d.rowptr;
@@ -420,6 +426,7 @@ int b200_rmcl_iter(int maxIter, double eps, const int* IG, const int* JG, const 
   rc = upload(IT, JT, T, n, n, nnzT, &dT);
   if (rc) { release(dG); return rc; }
   int it = 0;
+  double prev_ch = 0.0;
   for (; it < maxIter; ++it) {
     DevCSR dN;
     double ch = 0.0;
@@ -428,8 +435,11 @@ int b200_rmcl_iter(int maxIter, double eps, const int* IG, const int* JG, const 
     release(dT);  // Mt.dispose(); Mt = newMt  (nlibs/qrmcl.cc:72-73)
     dT = dN;
     if (chaos_hist) chaos_hist[it] = ch;
-    if (eps > 0 && ch < eps) { ++it; break; }
+    if (rmcl_converged(ch, prev_ch, it, eps)) { ++it; break; }
+    prev_ch = ch;
   }
+  // Mt.makeOrdered() — what the reference's drivers do before comparing (nrmcl.cc:25-26)
+  if (!rc) rc = sort_rows_device(&dT);
   if (!rc) {
     if (dT.nnz > INT_MAX) { set_error("nnz exceeds INT_MAX"); rc = B200_ERR_INT32_OVERFLOW; }
     else rc = download_rows(dT, 0, n, IM, JM, M, nnzM);

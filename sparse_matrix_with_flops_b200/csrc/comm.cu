@@ -135,6 +135,7 @@ int b200_rmcl_iter_sharded(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* 
   B200_CUDA(cudaEventCreate(&e0));
   B200_CUDA(cudaEventCreate(&e1));
   int it = 0, rc = B200_OK;
+  double prev_ch = 0.0;
   for (; it < maxIter; ++it) {
     B200_CUDA(cudaEventRecord(e0, st));
     // 1. flops-balanced cut points (identical on every rank: same inputs, same arithmetic)
@@ -198,8 +199,10 @@ int b200_rmcl_iter_sharded(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* 
     B200_CUDA(cudaStreamSynchronize(st));
     if (ms_per_iter) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_per_iter[it] = ms; }
     if (chaos_hist) chaos_hist[it] = ch;
-    if (eps > 0 && ch < eps) { ++it; break; }
+    if (rmcl_converged(ch, prev_ch, it, eps)) { ++it; break; }
+    prev_ch = ch;
   }
+  if (!rc) rc = sort_rows_device(&cur);  // Mt.makeOrdered() (nrmcl.cc:25-26)
   (*Mt_io)->d = cur;
   if (iters_done) *iters_done = it;
   dfree(d_prefix); dfree(d_meta); dfree(d_chaos);

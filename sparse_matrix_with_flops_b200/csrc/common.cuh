@@ -67,12 +67,25 @@ inline void dfree(T* p) {
   if (p) cudaFreeAsync((void*)p, ctx().stream);
 }
 
+// Stopping rule of the rMCL loops (not in the reference, whose loop is fixed-count,
+// nlibs/qrmcl.cc:31): with eps > 0 stop after the first iteration whose chaos is < eps or moved
+// by less than eps since the previous one (an rMCL fixed point keeps fractional rows, so its
+// chaos settles at a non-zero value).  oracle/oracle.c states the same rule.
+inline bool rmcl_converged(double ch, double prev, int it, double eps) {
+  if (!(eps > 0)) return false;
+  const double d = ch > prev ? ch - prev : prev - ch;
+  return ch < eps || (it > 0 && d < eps);
+}
+
 // mode of the row pipeline
 enum Mode { MODE_SPGEMM = 0, MODE_RMCL = 1 };
 
 // Core pipeline (spgemm.cu): C = A[row_lo:row_hi) x B, or the fused rMCL step.
 int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode,
                  DevCSR* C, double* chaos, b200_stats* stats);
+
+// CSR::makeOrdered on the device (spgemm.cu)
+int sort_rows_device(DevCSR* d);
 
 // flops prefix on device (spgemm.cu)
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,

@@ -48,14 +48,13 @@ constexpr int SB_W1K = 2;     // P <= 512
 constexpr int SB_W4K = 3;     // P <= 2048
 constexpr int SB_W16K = 4;    // P <= 8192
 constexpr int SB_BITMAP = 5;  // larger
-constexpr int NSBINS = 6;
 // numeric bins (by nnz(C_i))
 constexpr int NB_NONE = 0;    // empty row
 constexpr int NB_W64 = 1;
 constexpr int NB_W256 = 2;
 constexpr int NB_W1K = 3;
-constexpr int NB_BITMAP = 4;
-constexpr int NNBINS = 5;
+constexpr int NB_W2K = 4;
+constexpr int NB_BITMAP = 5;
 
 __host__ __device__ inline int sym_bin_of(long long P, int annz) {
   if (P == 0 || annz <= 1) return SB_NONE;
@@ -70,6 +69,7 @@ __host__ __device__ inline int num_bin_of(int cnt) {
   if (cnt <= 64) return NB_W64;
   if (cnt <= 256) return NB_W256;
   if (cnt <= 1024) return NB_W1K;
+  if (cnt <= 2048) return NB_W2K;
   return NB_BITMAP;
 }
 
@@ -336,16 +336,15 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
     }
   }
 
-  // ---- sort (column, slot) pairs ascending by column
-  unsigned long long* sb = (unsigned long long*)keys;
-  int n2 = 1;
-  while (n2 < cnt) n2 <<= 1;
-  for (int k = lane; k < n2; k += 32)
-    sb[k] = (k < cnt) ? (((unsigned long long)(unsigned)cols[k] << 32) | (unsigned)k) : ~0ull;
-  __syncwarp();
-  warp_bitonic_sort(sb, n2, lane);
-
   if (!RMCL) {
+    // ---- sort (column, slot) pairs ascending by column, then write the row
+    unsigned long long* sb = (unsigned long long*)keys;
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    for (int k = lane; k < n2; k += 32)
+      sb[k] = (k < cnt) ? (((unsigned long long)(unsigned)cols[k] << 32) | (unsigned)k) : ~0ull;
+    __syncwarp();
+    warp_bitonic_sort(sb, n2, lane);
     const int64_t ob = Crp[i];
     for (int k = lane; k < cnt; k += 32) {
       const unsigned long long e = sb[k];
@@ -355,30 +354,31 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
     return;
   }
 
-  // ---- fused rMCL epilogue, in ascending-column order
-  // (arrayInflationR2 / arrayMaxSum / computeThreshold / arrayThreshPruneNormalize,
-  //  nlibs/tools/util.cc:41-45, 21-31, 4-9, 47-69)
-  double* sv = (double*)cols;  // cols+slot regions: fp64[CAP]
+  // ---- fused rMCL epilogue in the reference's own order.  cols[]/vals[] hold the row in
+  // FIRST-TOUCH order, exactly the layout static_omp_CSR_RMCL_OneStep works on
+  // (nlibs/static_omp_csr_kernel.cc:256-271), so the sequential sums below reproduce
+  // arrayMaxSum (util.cc:21-31) and arrayThreshPruneNormalize (util.cc:47-69) bit for bit.
+  // Every lane runs the same serial chain on broadcast shared-memory reads (no divergence,
+  // no shuffle); other warps hide its latency.
+  for (int k = lane; k < cnt; k += 32) { const double v = vals[k]; vals[k] = __dmul_rn(v, v); }
   __syncwarp();
-  double psum = 0.0, pmax = 0.0;
-  for (int k = lane; k < cnt; k += 32) {
-    const double v = vals[(unsigned)(sb[k] & 0xffffffffu)];
-    const double v2 = __dmul_rn(v, v);
-    sv[k] = v2;
-    psum = __dadd_rn(psum, v2);
-    pmax = fmax(pmax, v2);
+  double rmax = 0.0, rsum = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < cnt; ++k) {
+    const double v = vals[k];
+    if (rmax < v) rmax = v;
+    rsum = __dadd_rn(rsum, v);
   }
-  const double rsum = warp_sum(psum), rmax = warp_max(pmax);
   const double thresh = compute_threshold(__ddiv_rn(rsum, (double)cnt), rmax);
-  __syncwarp();
-  double ksum_p = 0.0;
-  int kept_p = 0;
-  for (int k = lane; k < cnt; k += 32) {
-    const double v2 = sv[k];
-    if (v2 >= thresh) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
+  double ksum = 0.0;
+  int kept = 0;
+#pragma unroll 4
+  for (int k = 0; k < cnt; ++k) {
+    const double v = vals[k];
+    const bool keep = v >= thresh;
+    ksum = keep ? __dadd_rn(ksum, v) : ksum;
+    kept += keep ? 1 : 0;
   }
-  const double ksum = warp_sum(ksum_p);
-  const int kept = warp_sum_int(kept_p);
   unsigned long long off = 0;
   if (lane == 0) off = atomicAdd(ro.cursor, (unsigned long long)kept);
   off = (unsigned long long)shfl64((long long)off, 0);
@@ -386,12 +386,13 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
   int written = 0;
   for (int k0 = 0; k0 < cnt; k0 += 32) {
     const int k = k0 + lane;
-    const bool keep = (k < cnt) && (sv[k] >= thresh);
+    const double v = (k < cnt) ? vals[k] : 0.0;
+    const bool keep = (k < cnt) && (v >= thresh);
     const unsigned km = __ballot_sync(FULL, keep);
     if (keep) {
-      const double w = __ddiv_rn(sv[k], ksum);
+      const double w = __ddiv_rn(v, ksum);
       const long long o = (long long)off + written + __popc(km & lanemask_lt());
-      ro.arena_col[o] = (int)(sb[k] >> 32);
+      ro.arena_col[o] = cols[k];
       ro.arena_val[o] = w;
       sq_p = __dadd_rn(sq_p, __dmul_rn(w, w));
     }
@@ -749,6 +750,34 @@ constexpr int BT_BIG = 1024;
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
+// CSR::makeOrdered on the device (nlibs/CSR.cc:73-86): sort every row by column.  Runs once
+// at the end of an rMCL loop — not on the per-iteration path — so it uses the CUB segmented
+// sort as plain library plumbing.
+int sort_rows_device(DevCSR* d) {
+  Ctx& c = ctx();
+  if (d->nnz == 0 || d->rows == 0) return B200_OK;
+  int* col2 = nullptr;
+  double* val2 = nullptr;
+  B200_CUDA(dalloc(&col2, (size_t)d->nnz));
+  B200_CUDA(dalloc(&val2, (size_t)d->nnz));
+  void* tmp = nullptr;
+  size_t tb = 0;
+  cub::DeviceSegmentedSort::SortPairs(nullptr, tb, d->col, col2, d->val, val2, d->nnz, d->rows,
+                                      d->rowptr, d->rowptr + 1, c.stream);
+  B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, c.stream));
+  cub::DeviceSegmentedSort::SortPairs(tmp, tb, d->col, col2, d->val, val2, d->nnz, d->rows,
+                                      d->rowptr, d->rowptr + 1, c.stream);
+  B200_CUDA(cudaGetLastError());
+  cudaFreeAsync(tmp, c.stream);
+  dfree(d->col);
+  dfree(d->val);
+  d->col = col2;
+  d->val = val2;
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,
                         int64_t* d_prefix) {
   Ctx& c = ctx();
@@ -971,7 +1000,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
 
   // ---- 5. numeric per bin
-  auto launch_num_warp = [&](int bin, auto kernel, int CAP) -> int {
+  auto launch_num_warp = [&](int bin, auto kernel, int CAP, int WPB) -> int {
     const int cntb = nb.cnt[bin];
     if (!cntb) return B200_OK;
     const size_t smem = (size_t)WPB * 24 * CAP;
@@ -984,13 +1013,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     return B200_OK;
   };
   if (mode == MODE_SPGEMM) {
-    if ((rc = launch_num_warp(NB_W64, k_num_warp<64, false>, 64))) return rc;
-    if ((rc = launch_num_warp(NB_W256, k_num_warp<256, false>, 256))) return rc;
-    if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, false>, 1024))) return rc;
+    if ((rc = launch_num_warp(NB_W64, k_num_warp<64, false>, 64, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W256, k_num_warp<256, false>, 256, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, false>, 1024, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, false>, 2048, 4))) return rc;
   } else {
-    if ((rc = launch_num_warp(NB_W64, k_num_warp<64, true>, 64))) return rc;
-    if ((rc = launch_num_warp(NB_W256, k_num_warp<256, true>, 256))) return rc;
-    if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, true>, 1024))) return rc;
+    if ((rc = launch_num_warp(NB_W64, k_num_warp<64, true>, 64, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W256, k_num_warp<256, true>, 256, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, true>, 1024, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, true>, 2048, 4))) return rc;
   }
   if (nbig_num) {
     const int grid = std::min(nbig_num, c.sm_count);

@@ -54,7 +54,7 @@ def test_spgemm_golden(gpu, golden, name):
 def test_rmcl_golden(gpu, golden, name):
     r, c = golden[name + "_A_shape"]
     A = gpu.CSR(golden[name + "_A_V"], golden[name + "_A_J"], golden[name + "_A_I"], int(r), int(c))
-    step = M_of(A.staticOmpRmclOneStep(A))
+    step = M_of(A.staticOmpRmclOneStep(A).makeOrdered())
     ol.assert_same(step, ol.M(golden[name + "_step_sorted_I"], golden[name + "_step_sorted_J"],
                               golden[name + "_step_sorted_V"], int(r), int(c)), TOL, name + " step")
     Mt, iters, hist = gpu.gpuRmclIter(6, A, A)
@@ -85,6 +85,7 @@ def test_rmcl_synthetic(gpu, name, make):
     A = make(gpu)
     want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
     step = A.staticOmpRmclOneStep(A)
+    step.makeOrdered()
     ol.assert_same(M_of(step), want1, TOL, name + " one step")
     assert abs(step.chaos - ol.o_chaos(want1)) <= 1e-12
     want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 8)
@@ -104,6 +105,23 @@ def test_small_rows_are_bit_identical(gpu):
     A = gpu.synth_stencil27(10, 9, 8)
     got, want = gpu_spgemm(gpu, A, A), want_spgemm(A, A)
     assert np.array_equal(got.V.view(np.int64), want.V.view(np.int64))
+
+
+@pytest.mark.parametrize("make", [lambda s: s.synth_stencil27(10, 9, 8), lambda s: s.synth_planted(3000, 10, 16, 2, 1)])
+def test_rmcl_hash_bins_are_bit_identical_in_reference_order(gpu, make):
+    """Rows of <= 2048 distinct columns go through the warp hash bins, which keep the
+    reference's first-touch order and run its row math sequentially: the raw (unsorted) step
+    output and 8 chained iterations equal the reference's bit for bit."""
+    A = make(gpu)
+    raw = ol.o_rmcl_onestep(M_of(A), M_of(A))
+    got = M_of(A.staticOmpRmclOneStep(A))
+    assert np.array_equal(got.I, raw.I) and np.array_equal(got.J, raw.J)
+    assert np.array_equal(got.V.view(np.int64), raw.V.view(np.int64))
+    want, _, _ = ol.o_rmcl_iter(M_of(A), M_of(A), 8)
+    ol.o_make_ordered(want)
+    Mt, _, _ = gpu.gpuRmclIter(8, A, A)
+    assert np.array_equal(Mt.colInd, want.J)
+    assert np.array_equal(Mt.values.view(np.int64), want.V.view(np.int64))
 
 
 def test_rmcl_to_convergence(gpu):
@@ -214,6 +232,7 @@ def test_properties_at_scale(gpu):
     np.add.at(got_rs, rowid, C.values)
     assert np.allclose(got_rs, want_rs, rtol=1e-12, atol=0)
     dM, chaos = gpu.gpuRmclOneStep(dA, dA)
+    dM.makeOrdered()
     Mt = dM.toCpuCSR()
     dM.deviceDispose()
     dA.deviceDispose()
