@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the hot path (BASELINE.json `metric`).
+
+Workload (config.workload): single SpGEMM C = A·A on a synthetic directed R-MAT graph, scale 20,
+edge factor 16 (BASELINE.json configs[1]); rmclInit semantics (self loops, values 1/rowcount).
+A "step" is one whole pass of the path over that input: flops analysis → binning → symbolic →
+row offsets → numeric (sorted columns), result left in HBM.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]      one JSON line from rank 0
+  python bench.py --impl reference ...                       the reference's OpenMP CPU path
+
+* value       2·P·K / t, P = intermediate products (counted by the flops-analysis kernel), t =
+              CUDA-event time of K steps on the library's stream, max over ranks; operands
+              resident in HBM.  N > 1: the rows of A are cut into N contiguous blocks of equal
+              products (arrayEqualPartition64), rank r computes block r against the full B;
+              no collective on the data path; total work fixed => "scaling": "strong".
+* e2e         the same product through the reference-facing host-buffer entry point
+              b200_spgemm_csr (malloc'd int CSR in and out, include/b200_spgemm.h), H2D and
+              D2H copies inside the timed region.  nnz(C) = 9.7e9 exceeds the reference's
+              `int` CSR, so the caller walks row blocks (IA+lo, m=hi-lo) cut so
+              that every block's products (an upper bound of its nnz) fit an int.
+* roofline    the kernel with the largest share of the step: algorithmic bytes of the rows it
+              processed ÷ its CUDA-event duration (b200_stats.ms_*_bin), against the measured
+              HBM copy bandwidth of MEASURED_PEAKS.json.
+* cpu_baseline / --impl reference
+              the UNMODIFIED reference flops_omp_CSR_SpMM (oracle/_ref/libref.so, built by
+              oracle/Makefile from /root/reference) — or the C restatement oracle/liboracle.so
+              when that file is absent — on all host cores, on a bounded row sample of the same
+              product (every q-th row of A against the full B).
+
+Nothing on the measured GPU path touches oracle/.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spgemm_gflops"
+UNIT = "GFLOP/s"
+L2_BYTES = 126 * 1024 * 1024
+
+# numeric / symbolic bin names (sparse_matrix_with_flops_b200/csrc/spgemm.cu)
+SYM_KERNELS = {1: "k_sym_warp<256>", 2: "k_sym_warp<1024>", 3: "k_sym_warp<4096>",
+               4: "k_sym_warp<16384>", 5: "k_sym_bitmap"}
+NUM_KERNELS = {1: "k_num_warp<64>", 2: "k_num_warp<256>", 3: "k_num_warp<1024>",
+               4: "k_num_warp<2048>", 5: "k_num_bitmap"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="rmat20",
+                    help="rmat<scale> (directed, edge factor 16) | stencil<g> (g^3 27-point)")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
+    ap.add_argument("--no-cpu", action="store_true", help="development: skip the CPU baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def make_workload(smf, name):
+    if name.startswith("rmat"):
+        scale = int(name[4:])
+        A = smf.synth_rmat(scale, 16, 12345, False)
+        desc = "C=A*A, R-MAT scale %d edge factor 16 directed (a,b,c,d=.57,.19,.19,.05), seed 12345" % scale
+    elif name.startswith("stencil"):
+        g = int(name[7:])
+        A = smf.synth_stencil27(g, g, g)
+        desc = "C=A*A, 27-point stencil on a %d^3 grid" % g
+    else:
+        raise SystemExit("unknown workload " + name)
+    return A, desc
+
+
+def host_flops_prefix(A):
+    """Per-row intermediate products of A·A as an exclusive prefix (host numpy; used by the
+    reference arm and to cut row blocks for the host-buffer API)."""
+    rowlen = np.diff(A.rowPtr).astype(np.int64)
+    per_entry = rowlen[A.colInd]
+    cs = np.concatenate([[0], np.cumsum(per_entry)])
+    return cs[A.rowPtr.astype(np.int64)]
+
+
+# ---- CPU baseline (checker libraries; never on the GPU path) --------------------------------
+
+def row_sample(A, q, r=0):
+    """Rows r, r+q, r+2q, ... of A as a CSR over the same columns."""
+    rows = np.arange(r, A.rows, q, dtype=np.int64)
+    starts, ends = A.rowPtr[rows].astype(np.int64), A.rowPtr[rows + 1].astype(np.int64)
+    lens = ends - starts
+    I = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    idx = np.repeat(starts - I[:-1], lens) + np.arange(int(I[-1]), dtype=np.int64)
+    return I, np.ascontiguousarray(A.colInd[idx]), np.ascontiguousarray(A.values[idx]), len(rows)
+
+
+class CpuArm:
+    """flops_omp_CSR_SpMM of the reference (kind 'reference') or the oracle port (kind 'port')."""
+
+    def __init__(self, A, target_products=2.5e9):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        self.ol = ol
+        self.A = A
+        prefix = host_flops_prefix(A)
+        P = int(prefix[-1])
+        self.q = max(1, int(round(P / target_products)))
+        self.I, self.J, self.V, self.m = row_sample(A, self.q)
+        rowlen = np.diff(A.rowPtr).astype(np.int64)
+        self.products = int(rowlen[self.J].sum())
+        self.kind = "reference" if os.path.exists(ol.REF_SO) else "port"
+        self.cores = os.cpu_count()
+        self.sample = ("rows 0,%d,%d,... of A (%d rows, %d of %d products) x full B" %
+                       (self.q, 2 * self.q, self.m, self.products, P))
+
+    def step_ms(self):
+        A, ol = self.A, self.ol
+        ip, dp = ol.ip, ol.dp
+        _i, _d = ol._i, ol._d
+        if self.kind == "reference":
+            r = ol.ref()
+            nnzc = C.c_longlong(0)
+            self.cores = r.ref_num_threads()
+            ms = r.ref_spgemm_timed(3, _i(self.I), _i(self.J), _d(self.V), int(self.I[-1]),
+                                    _i(A.rowPtr), _i(A.colInd), _d(A.values), A.nnz, self.m,
+                                    A.cols, A.cols, 512, 1, C.byref(nnzc))
+            return float(ms)
+        o = ol.oracle()
+        IC, JC, Cv, n = ip(), ip(), dp(), C.c_int()
+        t0 = time.perf_counter()
+        rc = o.oracle_spgemm(_i(self.I), _i(self.J), _d(self.V), _i(A.rowPtr), _i(A.colInd),
+                             _d(A.values), self.m, A.cols, C.byref(IC), C.byref(JC), C.byref(Cv),
+                             C.byref(n))
+        ms = (time.perf_counter() - t0) * 1e3
+        assert rc == 0, rc
+        for p in (IC, JC, Cv):
+            o.oracle_free(C.cast(p, C.c_void_p))
+        return ms
+
+    def gflops(self, ms):
+        return 2.0 * self.products / (ms * 1e-3) / 1e9
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import sparse_matrix_with_flops_b200 as smf  # input generator only (host code)
+    A, desc = make_workload(smf, args.workload)
+    arm = CpuArm(A)
+    for _ in range(args.warmup):
+        arm.step_ms()
+    times = [arm.step_ms() for _ in range(args.steps)]
+    ms = sum(times) / len(times)
+    val = arm.gflops(ms)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "timing": "omp_get_wtime around flops_omp_CSR_SpMM, thread scratch allocated outside"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                         "sample": arm.sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- GPU arm -----------------------------------------------------------------------------------
+
+def kernel_bytes(kind, rows, products, nnzA, nnzC):
+    """ALGORITHMIC bytes of one launch (SURVEY.md §8d per-unit figures,
+    int32 index + fp64 value): numeric = A rows (12/entry + 4/row) + gathered B rows (12/product
+    + 8 of rowptr per A entry) + C rows (12/entry + 4/row); symbolic reads indices only and
+    writes one count per row."""
+    if kind == "num":
+        return 12 * nnzA + 4 * rows + 12 * products + 8 * nnzA + 12 * nnzC + 4 * rows
+    return 4 * nnzA + 4 * rows + 4 * products + 8 * nnzA + 4 * rows
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import sparse_matrix_with_flops_b200 as smf
+    from sparse_matrix_with_flops_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    smf.init(local)  # raises without a CUDA device: there is no CPU fallback
+    lib = _lib.load()
+    sp = C.c_void_p()
+    _lib.check(lib.b200_stream(C.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    A, desc = make_workload(smf, args.workload)
+    dA = A.toGpuCSR()
+    prefix = smf.flops_prefix(dA, dA)
+    P = int(prefix[-1])
+    ends = smf.arrayEqualPartition64(prefix, world)
+    lo, hi = int(ends[rank]), int(ends[rank + 1])
+
+    acc = {"sym": np.zeros(16), "num": np.zeros(16), "launches": 0, "last": None}
+
+    def step(record):
+        dC, st = smf.gpuSpMMWrapper(dA, dA, lo, hi, want_stats=True)
+        dC.deviceDispose()
+        if record:
+            acc["sym"] += np.array(st["ms_sym_bin"])
+            acc["num"] += np.array(st["ms_num_bin"])
+            acc["launches"] += st["launches"]
+            acc["last"] = st
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total, float(acc["launches"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(tmax[0]), int(t[1])
+    else:
+        launches = int(t[1])
+    ms_step = ms_total / args.steps
+    value = 2.0 * P / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (rank 0's launches) -----------------------------
+    st = acc["last"]
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    cands = []
+    for b, nm in SYM_KERNELS.items():
+        if acc["sym"][b] > 0:
+            cands.append((acc["sym"][b] / args.steps, "sym", b, nm))
+    for b, nm in NUM_KERNELS.items():
+        if acc["num"][b] > 0:
+            cands.append((acc["num"][b] / args.steps, "num", b, nm))
+    cands.sort(reverse=True)
+    kms, kind, b, kname = cands[0]
+    if kind == "num":
+        kb = kernel_bytes("num", st["bins_rows"][b], st["num_bin_products"][b], st["num_bin_nnzA"][b],
+                          st["num_bin_nnzC"][b])
+    else:
+        kb = kernel_bytes("sym", st["sym_bin_rows"][b], st["sym_bin_products"][b], st["sym_bin_nnzA"][b], 0)
+    achieved = kb / (kms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(kname)
+    nnzC = st["nnz_out"] if world == 1 else None
+    step_bytes = None
+    if world == 1:
+        step_bytes = kernel_bytes("num", A.rows, P, A.nnz, st["nnz_out"])
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
+                "kernel_algorithmic_bytes": kb,
+                "step_algorithmic_bytes": step_bytes,
+                "step_frac": (step_bytes / (ms_step * 1e-3) / 1e9 / peak) if step_bytes else None,
+                "kernels_ms": {nm: round(ms_, 4) for ms_, _, _, nm in cands}}
+
+    # ---- e2e through the host-buffer C-ABI ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        arm = CpuArm(A)
+        arm.step_ms()
+        ms = min(arm.step_ms(), arm.step_ms())
+        cpu = {"value": arm.gflops(ms), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+               "sample": arm.sample, "ms": ms}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "rows": A.rows, "nnzA": A.nnz, "products": P, "nnzC": nnzC,
+                       "partition": "flops-balanced contiguous row blocks, 1 per GPU",
+                       "l2": "no flush: inputs (%.0f MB) and output exceed the %d MB L2" % (
+                           (12 * A.nnz + 8 * A.rows) / 1e6, L2_BYTES // (1024 * 1024))},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dA.deviceDispose()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
+    """The reference-facing call with HOST buffers: b200_spgemm_csr per row block (IA+lo,
+    m=hi-lo), blocks cut on the host so that each block's product count fits an int."""
+    from sparse_matrix_with_flops_b200 import _lib
+    ip, dp = _lib.c_int_p, _lib.c_double_p
+    prefix = host_flops_prefix(A)
+    mine = int(prefix[hi] - prefix[lo])
+    nblk = max(1, -(-mine // 2_000_000_000))
+    local_prefix = (prefix[lo:hi + 1] - prefix[lo]).astype(np.int64)
+    cuts = smf.arrayEqualPartition64(local_prefix, nblk) + lo
+    IA, JA, VA = A.rowPtr, A.colInd, A.values
+    h2d = d2h = 0
+
+    def one():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for b in range(nblk):
+            r0, r1 = int(cuts[b]), int(cuts[b + 1])
+            if r1 <= r0:
+                continue
+            IC, JC, Cv, nnzC = ip(), ip(), dp(), C.c_int(0)
+            ia = IA[r0:r1 + 1]  # a view: absolute offsets into JA / VA, as the reference allows
+            _lib.check(lib.b200_spgemm_csr(ia.ctypes.data_as(ip), JA.ctypes.data_as(ip),
+                                           VA.ctypes.data_as(dp), A.nnz, IA.ctypes.data_as(ip),
+                                           JA.ctypes.data_as(ip), VA.ctypes.data_as(dp), A.nnz,
+                                           C.byref(IC), C.byref(JC), C.byref(Cv), C.byref(nnzC),
+                                           r1 - r0, A.cols, A.cols))
+            h2d += 4 * (r1 - r0 + 1) + 12 * A.nnz + 4 * (A.rows + 1) + 12 * A.nnz
+            d2h += 4 * (r1 - r0 + 1) + 12 * nnzC.value
+            for p in (IC, JC, Cv):
+                lib.b200_host_free(C.cast(p, C.c_void_p))
+
+    one()  # warm-up (page-faults the pools, loads the kernels)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        one()
+    barrier()
+    sec = (time.perf_counter() - t0) / args.e2e_steps
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    sec = float(t[0])
+    return {"value": 2.0 * P / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
+            "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
+            "warmup": 1, "row_blocks": nblk,
+            "api": "b200_spgemm_csr (host malloc'd int CSR in/out), wall clock incl. H2D + D2H"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

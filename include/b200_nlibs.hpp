@@ -1,0 +1,400 @@
+// b200_nlibs.hpp — header-only C++ host layer that keeps the reference's API surface for the
+// hot path and forwards to the C-ABI in b200_spgemm.h.  It contains no algorithm.
+//
+// A program written against the reference's nlibs (struct CSR, CSR::flops_spmm / omp_spmm /
+// somp_spmm, CSR::staticOmpRmclOneStep, CSR::toGpuCSR / toCpuCSR / deviceDispose,
+// gpuSpMMWrapper, gpuRmclIter, rmclInit, RMCL, PCSR) compiles against this header after
+// `using namespace b200::nlibs;` and links libb200spgemm.so.  Reference interfaces mirrored
+// (paths relative to the reference root):
+//   struct CSR                         nlibs/CSR.h:23-379
+//   CSR::spmm/flops_spmm/omp_spmm/...  nlibs/CSR.cc:59-71,108-194
+//   CSR::*RmclOneStep                  nlibs/CSR.cc:251-305
+//   CSR::toGpuCSR/toCpuCSR/deviceDispose  nlibs/CSR.cc:342-379
+//   flops_omp_CSR_SpMM, omp_CSR_SpMM   nlibs/cpu_csr_kernel.h:73-76,95-98
+//   static_omp_CSR_RMCL_OneStep        nlibs/cpu_csr_kernel.h:194-197
+//   gpuRmclIter, gpuSpMMWrapper        nlibs/gpus/gpu_csr_kernel.h:5-6
+//   rmclInit, RMCL, RunOptions         nlibs/qrmcl.h:8-24
+//   COO (in-memory part)               nlibs/COO.h:6-26
+//   PCSR                               nlibs/PCSR.h:5-101
+//
+// Error behaviour follows the reference: failures print the message and exit(EXIT_FAILURE)
+// (nlibs/tools/qmalloc.h:14-16, nlibs/gpus/cuda_handle_error.h:7-13); dimension mismatches
+// assert (nlibs/CSR.cc:183).  Ownership follows the reference too: host arrays are malloc()
+// blocks released by dispose(); a device CSR is released by deviceDispose().
+#ifndef B200_NLIBS_HPP_
+#define B200_NLIBS_HPP_
+
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <numeric>
+#include <utility>
+#include <vector>
+#include "b200_spgemm.h"
+
+namespace b200 {
+namespace nlibs {
+
+typedef double QValue;  // the reference built with -DQValue=double -DFDOUBLE (tools/macro.h:3-6)
+struct thread_data_t;   // accepted and ignored: the device path needs no per-thread scratch
+
+// B200 joins the reference's list (nlibs/qrmcl.h:8); the CPU variants all map to it here.
+enum RunOptions { SEQ, OMP, GPU, CILK, SOMP, MKL, SFOMP, HYB, B200 };
+
+inline void b200_check(int rc, const char* what) {
+  if (rc != B200_OK) {
+    fprintf(stderr, "%s failed: %s\n", what, b200_last_error());
+    exit(EXIT_FAILURE);
+  }
+}
+inline void b200_ensure_init() {
+  static bool done = false;
+  if (!done) {
+    const char* dev = getenv("B200_DEVICE");
+    b200_check(b200_init(dev ? atoi(dev) : 0), "b200_init");
+    done = true;
+  }
+}
+
+struct CSR {
+  QValue* values;
+  int* colInd;
+  int* rowPtr;
+  int rows, cols, nnz;
+  // Device residency.  The reference reuses the same struct with cudaMalloc pointers
+  // (nlibs/CSR.cc:342-354); here a device CSR carries the opaque handle and null arrays.
+  b200_csr_t device;
+
+  CSR() : values(NULL), colInd(NULL), rowPtr(NULL), rows(0), cols(0), nnz(0), device(NULL) {}
+  CSR(QValue* values, int* colInd, int* rowPtr, int rows, int cols, int nnz)
+      : values(values), colInd(colInd), rowPtr(rowPtr), rows(rows), cols(cols), nnz(nnz), device(NULL) {}
+
+  void dispose() {
+    free(values); values = NULL;
+    free(colInd); colInd = NULL;
+    free(rowPtr); rowPtr = NULL;
+  }
+  void deviceDispose() {
+    if (device) { b200_csr_free(device); device = NULL; }
+  }
+  int rowCount(int rowId) const { return rowPtr[rowId + 1] - rowPtr[rowId]; }
+
+  CSR deepCopy() const {
+    CSR o;
+    o.rows = rows; o.cols = cols; o.nnz = nnz;
+    o.rowPtr = (int*)malloc(((size_t)rows + 1) * sizeof(int));
+    o.colInd = (int*)malloc(((size_t)nnz + 1) * sizeof(int));
+    o.values = (QValue*)malloc(((size_t)nnz + 1) * sizeof(QValue));
+    if (!o.rowPtr || !o.colInd || !o.values) { fprintf(stderr, "malloc failed\n"); exit(EXIT_FAILURE); }
+    memcpy(o.rowPtr, rowPtr, ((size_t)rows + 1) * sizeof(int));
+    memcpy(o.colInd, colInd, (size_t)nnz * sizeof(int));
+    memcpy(o.values, values, (size_t)nnz * sizeof(QValue));
+    return o;
+  }
+
+  // every entry of a row becomes 1/rowcount (nlibs/CSR.cc:88-95)
+  void averAndNormRowQValue() {
+    for (int i = 0; i < rows; ++i) {
+      const int cnt = rowPtr[i + 1] - rowPtr[i];
+      for (int p = rowPtr[i]; p < rowPtr[i + 1]; ++p) values[p] = 1.0 / cnt;
+    }
+  }
+
+  // ---- SpGEMM: every reference variant computes the same product ------------------------
+  CSR spmm(const CSR& B) const { return mul(B, false, NULL); }
+  CSR flops_spmm(const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
+  CSR omp_spmm(const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
+  CSR omp_spmm(thread_data_t*, const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
+  CSR somp_spmm(const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
+  CSR somp_spmm(thread_data_t*, const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
+
+  // ---- one rMCL iteration: this = Mgt, B = Mt (nlibs/CSR.cc:251-276) ---------------------
+  CSR ompRmclOneStep(const CSR& B, thread_data_t*, const int stride) const { (void)stride; return mul(B, true, NULL); }
+  CSR staticOmpRmclOneStep(const CSR& B, thread_data_t*, const int stride) const { (void)stride; return mul(B, true, NULL); }
+  CSR staticFairRmclOneStep(const CSR& B, const int stride) const { (void)stride; return mul(B, true, NULL); }
+  CSR rmclOneStepWithChaos(const CSR& B, double* chaos) const { return mul(B, true, chaos); }
+
+  // ---- host <-> device (nlibs/CSR.cc:342-371) ---------------------------------------------
+  CSR toGpuCSR() const {
+    b200_ensure_init();
+    CSR d;
+    d.rows = rows; d.cols = cols; d.nnz = nnz;
+    b200_check(b200_csr_upload(rowPtr, colInd, values, rows, cols, nnz, &d.device), "b200_csr_upload");
+    return d;
+  }
+  CSR toCpuCSR() const {
+    assert(device);
+    CSR h;
+    h.rows = rows; h.cols = cols;
+    b200_check(b200_csr_download(device, &h.rowPtr, &h.colInd, &h.values, &h.nnz), "b200_csr_download");
+    return h;
+  }
+
+  // per-row sort by column (nlibs/CSR.cc:73-86); host data, or the device kernel for a device CSR
+  void makeOrdered() {
+    if (device) { b200_check(b200_csr_sort_rows(device), "b200_csr_sort_rows"); return; }
+    std::vector<std::pair<int, QValue> > buf;
+    for (int i = 0; i < rows; ++i) {
+      const int s = rowPtr[i], e = rowPtr[i + 1];
+      buf.resize(e - s);
+      for (int p = s; p < e; ++p) buf[p - s] = std::make_pair(colInd[p], values[p]);
+      std::sort(buf.begin(), buf.end());
+      for (int p = s; p < e; ++p) { colInd[p] = buf[p - s].first; values[p] = buf[p - s].second; }
+    }
+  }
+
+  // Strict comparison on column-sorted matrices: shape, rowPtr and colInd exact, values within
+  // `rel` relative.  (The reference's isEqual, nlibs/CSR.h:195-245, uses an absolute 1e-7 and
+  // does not compare colInd; this one is the acceptance bar of BASELINE.json instead.)
+  bool isEqual(const CSR& B, double rel = 1e-12) const {
+    if (rows != B.rows || cols != B.cols || nnz != B.nnz) {
+      printf("shape/nnz differ: %d x %d nnz %d vs %d x %d nnz %d\n", rows, cols, nnz, B.rows, B.cols, B.nnz);
+      return false;
+    }
+    for (int i = 0; i <= rows; ++i)
+      if (rowPtr[i] != B.rowPtr[i]) { printf("rowPtr[%d] %d\t%d\n", i, rowPtr[i], B.rowPtr[i]); return false; }
+    for (int p = 0; p < nnz; ++p) {
+      if (colInd[p] != B.colInd[p]) { printf("colInd[%d] %d\t%d\n", p, colInd[p], B.colInd[p]); return false; }
+      if (fabs(values[p] - B.values[p]) > rel * fabs(B.values[p])) {
+        printf("values[%d] %.17g\t%.17g\n", p, values[p], B.values[p]);
+        return false;
+      }
+    }
+    return true;
+  }
+
+  // products of A x B, counted exactly (the reference's getSpMMFlops in this fork only counts
+  // rows with > 1024 products, nlibs/cpu_csr_kernel.cc:58-72)
+  long long spMMFlops(const CSR& B) const {
+    long long f = 0;
+    for (int p = 0; p < nnz; ++p) f += B.rowPtr[colInd[p] + 1] - B.rowPtr[colInd[p]];
+    return f;
+  }
+
+ private:
+  CSR mul(const CSR& B, bool rmcl, double* chaos) const {
+    assert(cols == B.rows);  // nlibs/CSR.cc:183
+    b200_ensure_init();
+    CSR c;
+    c.rows = rows; c.cols = B.cols;
+    if (rmcl)
+      b200_check(b200_rmcl_onestep_csr(rowPtr, colInd, values, nnz, B.rowPtr, B.colInd, B.values, B.nnz,
+                                       &c.rowPtr, &c.colInd, &c.values, &c.nnz, rows, cols, B.cols, chaos),
+                 "b200_rmcl_onestep_csr");
+    else
+      b200_check(b200_spgemm_csr(rowPtr, colInd, values, nnz, B.rowPtr, B.colInd, B.values, B.nnz,
+                                 &c.rowPtr, &c.colInd, &c.values, &c.nnz, rows, cols, B.cols),
+                 "b200_spgemm_csr");
+    return c;
+  }
+};
+
+// ---- the raw CSR-triple entry points (nlibs/cpu_csr_kernel.h:73-76, 95-98, 194-197) ---------
+inline void flops_omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                               const int IB[], const int JB[], const QValue B[], const int nnzB,
+                               int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                               const int n, const int stride) {
+  (void)stride;
+  b200_ensure_init();
+  b200_check(b200_spgemm_csr(IA, JA, A, nnzA, IB, JB, B, nnzB, &IC, &JC, &C, &nnzC, m, k, n),
+             "b200_spgemm_csr");
+}
+inline void omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                         const int IB[], const int JB[], const QValue B[], const int nnzB,
+                         int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                         const int n, const int stride) {
+  flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
+}
+inline void static_omp_CSR_RMCL_OneStep(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                                        const int IB[], const int JB[], const QValue B[], const int nnzB,
+                                        int*& IC, int*& JC, QValue*& C, int& nnzC, const int m,
+                                        const int k, const int n, const thread_data_t* thread_datas,
+                                        const int stride) {
+  (void)thread_datas; (void)stride;
+  b200_ensure_init();
+  b200_check(b200_rmcl_onestep_csr(IA, JA, A, nnzA, IB, JB, B, nnzB, &IC, &JC, &C, &nnzC, m, k, n, NULL),
+             "b200_rmcl_onestep_csr");
+}
+inline void omp_CSR_RMCL_OneStep(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                                 const int IB[], const int JB[], const QValue B[], const int nnzB,
+                                 int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                                 const int n, const thread_data_t* thread_datas, const int stride) {
+  static_omp_CSR_RMCL_OneStep(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, thread_datas, stride);
+}
+
+// ---- GPU slot (nlibs/gpus/gpu_csr_kernel.h:5-6) ----------------------------------------------
+// device in, device out
+inline CSR gpuSpMMWrapper(const CSR& dA, const CSR& dB) {
+  assert(dA.device && dB.device);
+  CSR dC;
+  b200_check(b200_spgemm_device(dA.device, dB.device, &dC.device, NULL), "b200_spgemm_device");
+  long long z = 0;
+  b200_csr_info(dC.device, &dC.rows, &dC.cols, &z);
+  dC.nnz = z > 2147483647LL ? -1 : (int)z;  // > INT_MAX: only the handle can describe it
+  return dC;
+}
+// host Mgt / Mt in, final host Mt out (sorted rows); Mt's old arrays are disposed like
+// `Mt.dispose(); Mt = newMt` (nlibs/qrmcl.cc:72-73)
+inline void gpuRmclIter(const int maxIter, const CSR Mgt, CSR& Mt, double eps = 0.0, int* itersDone = NULL,
+                        double* chaosHist = NULL) {
+  b200_ensure_init();
+  CSR out;
+  out.rows = Mgt.rows; out.cols = Mt.cols;
+  b200_check(b200_rmcl_iter(maxIter, eps, Mgt.rowPtr, Mgt.colInd, Mgt.values, Mgt.nnz, Mt.rowPtr, Mt.colInd,
+                            Mt.values, Mt.nnz, &out.rowPtr, &out.colInd, &out.values, &out.nnz, Mgt.rows,
+                            itersDone, chaosHist),
+             "b200_rmcl_iter");
+  Mt.dispose();
+  Mt = out;
+}
+
+// ---- COO, in-memory part (nlibs/COO.h:6-26, COO.cc:24-35,160-188,222-291) ---------------------
+class COO {
+ public:
+  int* cooRowIndex;
+  int* cooColIndex;
+  QValue* cooVal;
+  int rows, cols, nnz;
+  COO() : cooRowIndex(NULL), cooColIndex(NULL), cooVal(NULL), rows(0), cols(0), nnz(0) {}
+  COO(const QValue* const val, const int* const colIndex, const int* const rowIndex, const int rows,
+      const int cols, const int nnz)
+      : rows(rows), cols(cols), nnz(nnz) {
+    cooRowIndex = (int*)malloc(((size_t)nnz + 1) * sizeof(int));
+    cooColIndex = (int*)malloc(((size_t)nnz + 1) * sizeof(int));
+    cooVal = (QValue*)malloc(((size_t)nnz + 1) * sizeof(QValue));
+    memcpy(cooRowIndex, rowIndex, (size_t)nnz * sizeof(int));
+    memcpy(cooColIndex, colIndex, (size_t)nnz * sizeof(int));
+    memcpy(cooVal, val, (size_t)nnz * sizeof(QValue));
+  }
+  void dispose() {
+    free(cooRowIndex); free(cooColIndex); free(cooVal);
+    cooRowIndex = cooColIndex = NULL; cooVal = NULL;
+  }
+  // one (i,i,1.0) entry for every vertex without a diagonal entry; input must be duplicate free
+  // (SURVEY.md §8c input hazards)
+  void addSelfLoopIfNeeded() {
+    assert(rows == cols);
+    std::vector<char> has(rows, 0);
+    for (int e = 0; e < nnz; ++e) if (cooRowIndex[e] == cooColIndex[e]) has[cooRowIndex[e]] = 1;
+    int missing = 0;
+    for (int i = 0; i < rows; ++i) missing += !has[i];
+    cooRowIndex = (int*)realloc(cooRowIndex, ((size_t)nnz + missing + 1) * sizeof(int));
+    cooColIndex = (int*)realloc(cooColIndex, ((size_t)nnz + missing + 1) * sizeof(int));
+    cooVal = (QValue*)realloc(cooVal, ((size_t)nnz + missing + 1) * sizeof(QValue));
+    for (int i = 0; i < rows; ++i)
+      if (!has[i]) { cooRowIndex[nnz] = i; cooColIndex[nnz] = i; cooVal[nnz] = 1.0; ++nnz; }
+  }
+  void makeOrdered() const {
+    std::vector<int> perm(nnz);
+    std::iota(perm.begin(), perm.end(), 0);
+    const int* r = cooRowIndex; const int* c = cooColIndex;
+    std::sort(perm.begin(), perm.end(), [r, c](int x, int y) { return r[x] != r[y] ? r[x] < r[y] : c[x] < c[y]; });
+    std::vector<int> rr(nnz), cc(nnz);
+    std::vector<QValue> vv(nnz);
+    for (int e = 0; e < nnz; ++e) { rr[e] = cooRowIndex[perm[e]]; cc[e] = cooColIndex[perm[e]]; vv[e] = cooVal[perm[e]]; }
+    memcpy(cooRowIndex, rr.data(), (size_t)nnz * sizeof(int));
+    memcpy(cooColIndex, cc.data(), (size_t)nnz * sizeof(int));
+    memcpy(cooVal, vv.data(), (size_t)nnz * sizeof(QValue));
+  }
+  CSR toCSR() const {
+    CSR m;
+    m.rows = rows; m.cols = cols; m.nnz = nnz;
+    m.rowPtr = (int*)calloc((size_t)rows + 1, sizeof(int));
+    m.colInd = (int*)malloc(((size_t)nnz + 1) * sizeof(int));
+    m.values = (QValue*)malloc(((size_t)nnz + 1) * sizeof(QValue));
+    for (int e = 0; e < nnz; ++e) m.rowPtr[cooRowIndex[e] + 1]++;
+    for (int i = 0; i < rows; ++i) m.rowPtr[i + 1] += m.rowPtr[i];
+    std::vector<int> cur(m.rowPtr, m.rowPtr + rows);
+    for (int e = 0; e < nnz; ++e) {
+      const int p = cur[cooRowIndex[e]]++;
+      m.colInd[p] = cooColIndex[e];
+      m.values[p] = cooVal[e];
+    }
+    return m;
+  }
+};
+
+// nlibs/qrmcl.cc:126-134
+inline CSR rmclInit(COO& cooAt) {
+  cooAt.addSelfLoopIfNeeded();
+  cooAt.makeOrdered();
+  CSR Mt = cooAt.toCSR();
+  Mt.averAndNormRowQValue();
+  return Mt;
+}
+
+// RMCL (nlibs/qrmcl.cc:136-164) from an in-memory COO instead of a file name (file ingest is the
+// next row of SURVEY.md §8f); every RunOptions value runs the B200 path.
+inline CSR RMCL(COO& cooAt, int maxIters, RunOptions runOptions = B200, double eps = 0.0,
+                int* itersDone = NULL) {
+  (void)runOptions;
+  CSR Mt = rmclInit(cooAt);
+  CSR Mgt = Mt.deepCopy();
+  gpuRmclIter(maxIters, Mgt, Mt, eps, itersDone, NULL);
+  Mgt.dispose();
+  return Mt;
+}
+
+// ---- PCSR: c column stripes of width ceil(cols/c) (nlibs/PCSR.h:5-101, PCSR.cc:3-56) -----------
+struct PCSR {
+  int rows, cols;
+  int c;
+  CSR* blocks;
+  int stride() const { return (cols + c - 1) / c; }
+  int nnz() const { int t = 0; for (int b = 0; b < c; ++b) t += blocks[b].nnz; return t; }
+  PCSR(const CSR& csr, const int c) : rows(csr.rows), cols(csr.cols), c(c) {
+    blocks = (CSR*)malloc((size_t)c * sizeof(CSR));
+    const int w = stride();
+    std::vector<int> cnt(c, 0);
+    for (int p = 0; p < csr.nnz; ++p) cnt[csr.colInd[p] / w]++;
+    for (int b = 0; b < c; ++b) {
+      blocks[b] = CSR((QValue*)malloc(((size_t)cnt[b] + 1) * sizeof(QValue)),
+                      (int*)malloc(((size_t)cnt[b] + 1) * sizeof(int)),
+                      (int*)calloc((size_t)rows + 1, sizeof(int)), rows, std::min(w, cols - b * w), cnt[b]);
+    }
+    std::vector<int> at(c, 0);
+    for (int i = 0; i < rows; ++i) {
+      for (int p = csr.rowPtr[i]; p < csr.rowPtr[i + 1]; ++p) {
+        const int b = csr.colInd[p] / w;
+        blocks[b].colInd[at[b]] = csr.colInd[p] - b * w;
+        blocks[b].values[at[b]] = csr.values[p];
+        ++at[b];
+      }
+      for (int b = 0; b < c; ++b) blocks[b].rowPtr[i + 1] = at[b];
+    }
+  }
+  void dispose() {
+    for (int b = 0; b < c; ++b) blocks[b].dispose();
+    free(blocks);
+    blocks = NULL;
+  }
+  // C = A x this, stripe by stripe on the device, reassembled with global columns
+  // (correctTests/pcsrTest.cc:7-19)
+  CSR leftMultiply(const CSR& A) const {
+    std::vector<CSR> parts(c);
+    long long total = 0;
+    for (int b = 0; b < c; ++b) { parts[b] = A.spmm(blocks[b]); total += parts[b].nnz; }
+    CSR out((QValue*)malloc(((size_t)total + 1) * sizeof(QValue)), (int*)malloc(((size_t)total + 1) * sizeof(int)),
+            (int*)calloc((size_t)A.rows + 1, sizeof(int)), A.rows, cols, (int)total);
+    int at = 0;
+    const int w = stride();
+    for (int i = 0; i < A.rows; ++i) {
+      for (int b = 0; b < c; ++b)
+        for (int p = parts[b].rowPtr[i]; p < parts[b].rowPtr[i + 1]; ++p) {
+          out.colInd[at] = parts[b].colInd[p] + b * w;
+          out.values[at] = parts[b].values[p];
+          ++at;
+        }
+      out.rowPtr[i + 1] = at;
+    }
+    for (int b = 0; b < c; ++b) parts[b].dispose();
+    return out;
+  }
+};
+
+}  // namespace nlibs
+}  // namespace b200
+#endif  // B200_NLIBS_HPP_

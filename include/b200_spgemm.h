@@ -53,6 +53,14 @@ typedef struct b200_stats {
   long long nnz_unpruned; /* rMCL only: nnz before pruning (== nnz_out for SpGEMM)          */
   int launches;        /* kernels of this library launched by the call                      */
   int bins_rows[16];   /* rows per numeric bin (diagnostic)                                 */
+  /* Per-bin breakdown (bench.py's roofline leg): device time of each bin's symbolic and
+   * numeric kernel (CUDA events on the library stream around the launch), and the rows,
+   * intermediate products, nnz(A rows) and nnz(C rows) each bin processed.  Symbolic bins are
+   * keyed by products per row, numeric bins by nnz(C row); see DESIGN.md for the cut points. */
+  double ms_sym_bin[16];
+  double ms_num_bin[16];
+  long long sym_bin_rows[16], sym_bin_products[16], sym_bin_nnzA[16];
+  long long num_bin_products[16], num_bin_nnzA[16], num_bin_nnzC[16];
 } b200_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -62,6 +70,9 @@ typedef struct b200_stats {
 int b200_init(int device);
 int b200_finalize(void);
 const char* b200_last_error(void);
+/* The CUDA stream (a cudaStream_t) every kernel of this library is launched on, so that a
+ * harness can bracket calls with its own CUDA events. */
+int b200_stream(void** stream);
 /* Launch configuration facts, for the harness: SM count and device name. */
 int b200_device_info(int* sm_count, long long* hbm_bytes, char* name, int name_len);
 

@@ -29,11 +29,21 @@ class Stats(C.Structure):
         ("nnz_unpruned", C.c_longlong),
         ("launches", C.c_int),
         ("bins_rows", C.c_int * 16),
+        ("ms_sym_bin", C.c_double * 16),
+        ("ms_num_bin", C.c_double * 16),
+        ("sym_bin_rows", C.c_longlong * 16),
+        ("sym_bin_products", C.c_longlong * 16),
+        ("sym_bin_nnzA", C.c_longlong * 16),
+        ("num_bin_products", C.c_longlong * 16),
+        ("num_bin_nnzA", C.c_longlong * 16),
+        ("num_bin_nnzC", C.c_longlong * 16),
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "bins_rows"}
-        d["bins_rows"] = list(self.bins_rows)
+        d = {}
+        for k, t in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
         return d
 
 
@@ -42,6 +52,7 @@ SIGNATURES = {
     "b200_init": (C.c_int, [C.c_int]),
     "b200_finalize": (C.c_int, []),
     "b200_last_error": (C.c_char_p, []),
+    "b200_stream": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b200_device_info": (C.c_int, [c_int_p, c_ll_p, C.c_char_p, C.c_int]),
     "b200_spgemm_csr": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_int_p, c_double_p,
                                   C.c_int, C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p),

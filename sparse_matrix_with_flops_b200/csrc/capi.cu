@@ -150,6 +150,7 @@ int b200_init(int device) {
   strncpy(c.name, p.name, sizeof(c.name) - 1);
   B200_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   for (auto& ev : c.ev) B200_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : c.kev) B200_CUDA(cudaEventCreate(&ev));
   // keep freed blocks in the stream-ordered pool: per-iteration cudaMalloc was a cost centre of
   // the reference's GPU loop (nlibs/gpus/gpu_csr_kernel.cu:258-259)
   cudaMemPool_t pool;
@@ -165,9 +166,17 @@ int b200_finalize(void) {
   if (!c.ready) return B200_OK;
   cudaStreamSynchronize(c.stream);
   for (auto& ev : c.ev) { cudaEventDestroy(ev); ev = nullptr; }
+  for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   c.ready = false;
+  return B200_OK;
+}
+
+int b200_stream(void** stream) {
+  B200_REQUIRE_INIT();
+  if (!stream) { set_error("null argument"); return B200_ERR_BAD_ARG; }
+  *stream = (void*)ctx().stream;
   return B200_OK;
 }
 

@@ -35,6 +35,7 @@ struct Ctx {
   size_t hbm_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t kev[64] = {};  // per-kernel brackets: [2*b], [2*b+1] symbolic bin b; 32+ numeric
   char name[128] = {0};
 };
 Ctx& ctx();

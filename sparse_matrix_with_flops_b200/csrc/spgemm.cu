@@ -73,7 +73,14 @@ __host__ __device__ inline int num_bin_of(int cnt) {
   return NB_BITMAP;
 }
 
-__device__ __forceinline__ unsigned hash_col(int c) { return (unsigned)c * 107u; }
+// Fibonacci hashing: the slot is the TOP log2(H) bits of c * 2^32/phi.  (Taking low bits of a
+// product would make columns that differ by a multiple of H collide — exactly what a stencil on
+// a power-of-two grid produces.)
+template <int H>
+__device__ __forceinline__ unsigned hash_col(int c) {
+  static_assert((H & (H - 1)) == 0 && H >= 2, "table size must be a power of two");
+  return ((unsigned)c * 0x9E3779B1u) >> (32 - __builtin_ctz(H));
+}
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -158,6 +165,24 @@ k_bin_hist(const unsigned char* __restrict__ bin, int m, int* __restrict__ hist)
   if (threadIdx.x < 16 && s[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s[threadIdx.x]);
 }
 
+// per-bin totals for b200_stats: agg[b*3+0] += a[i], +1 += b[i], +2 += c[i] for bin[i]==b
+__global__ void __launch_bounds__(256)
+k_bin_aggregate(const unsigned char* __restrict__ bin, int m, const int64_t* __restrict__ Arp,
+                int row_lo, const long long* __restrict__ flops, const int* __restrict__ rownnz,
+                unsigned long long* __restrict__ agg) {
+  __shared__ unsigned long long s[48];
+  if (threadIdx.x < 48) s[threadIdx.x] = 0ull;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const int b = bin[i];
+    atomicAdd(&s[b * 3 + 0], (unsigned long long)flops[i]);
+    atomicAdd(&s[b * 3 + 1], (unsigned long long)(Arp[row_lo + i + 1] - Arp[row_lo + i]));
+    if (rownnz) atomicAdd(&s[b * 3 + 2], (unsigned long long)rownnz[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 48 && s[threadIdx.x]) atomicAdd(&agg[threadIdx.x], s[threadIdx.x]);
+}
+
 // scatter row ids into per-bin lists (cursor[b] starts at the bin's offset)
 __global__ void __launch_bounds__(256)
 k_bin_scatter(const unsigned char* __restrict__ bin, int m, int* __restrict__ cursor,
@@ -181,10 +206,11 @@ k_bin_scatter(const unsigned char* __restrict__ bin, int m, int* __restrict__ cu
 // All 32 lanes call it together; keys offered in one call are pairwise distinct (they come
 // from one B row), so a lane can only lose a slot to a DIFFERENT key.  Returns true if the
 // key was new; `h` is left at the key's slot.
-__device__ __forceinline__ bool warp_find_or_insert(int* keys, unsigned mask, int c, bool active,
-                                                    unsigned& h) {
+template <int H>
+__device__ __forceinline__ bool warp_find_or_insert(int* keys, int c, bool active, unsigned& h) {
+  constexpr unsigned mask = H - 1;
   bool done = !active, isnew = false;
-  h = hash_col(c) & mask;
+  h = hash_col<H>(c);
   while (true) {
     bool attempt = false;
     if (!done) {
@@ -233,7 +259,7 @@ k_sym_warp(const int* __restrict__ list, int count, int row_lo,
         const bool act = q < e;
         const int c = act ? __ldg(Bcol + q) : 0;
         unsigned h;
-        cnt += warp_find_or_insert(keys, H - 1, c, act, h) ? 1 : 0;
+        cnt += warp_find_or_insert<H>(keys, c, act, h) ? 1 : 0;
       }
     }
   }
@@ -319,7 +345,7 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
         double prod = 0.0;
         if (act) { c = __ldg(Bcol + q); prod = __dmul_rn(a, __ldg(Bval + q)); }
         unsigned h;
-        const bool isnew = warp_find_or_insert(keys, H - 1, c, act, h);
+        const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
         const unsigned newmask = __ballot_sync(FULL, isnew);
         if (isnew) {
           const int sl = cnt + __popc(newmask & lanemask_lt());
@@ -816,6 +842,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   C->rows = m;
   C->cols = n;
   B200_CUDA(cudaEventRecord(c.ev[0], st));
+  // per-kernel brackets (only when the caller asked for stats)
+  bool sym_timed[16] = {false}, num_timed[16] = {false};
+  auto tick = [&](int slot) { if (stats) cudaEventRecord(c.kev[slot], st); };
 
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
@@ -846,15 +875,17 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaEventRecord(c.ev[1], st));
 
   // ---- 2. symbolic per bin
-  const int WPB = 8;  // warps per block in the warp-per-row kernels
   auto launch_sym_warp = [&](int bin, auto kernel, int H, int WPB) -> int {
     const int cntb = sb.cnt[bin];
     if (!cntb) return B200_OK;
     const size_t smem = (size_t)WPB * H * sizeof(int);
     int r = set_smem(kernel, smem);
     if (r) return r;
+    tick(2 * bin);
     kernel<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(sb.d_list + sb.off[bin], cntb, row_lo,
                                                            A.rowptr, A.col, B.rowptr, B.col, d_cnt);
+    tick(2 * bin + 1);
+    sym_timed[bin] = true;
     ++launches;
     return B200_OK;
   };
@@ -886,6 +917,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if (store_bitmaps) B200_CUDA(dalloc(&d_bmstore, (size_t)nbig * nw64));
     if (!sym_smem || !num_smem)
       B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
+    tick(2 * SB_BITMAP);
+    sym_timed[SB_BITMAP] = true;
     if (sym_smem) {
       if ((rc = set_smem(k_sym_bitmap<BT_BIG, true>, bm_bytes))) return rc;
       k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, bm_bytes, st>>>(
@@ -896,6 +929,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, nw64,
           d_gscr, d_bmstore, d_cnt, d_work + 0);
     }
+    tick(2 * SB_BITMAP + 1);
     ++launches;
   }
   B200_CUDA(cudaGetLastError());
@@ -1006,9 +1040,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     const size_t smem = (size_t)WPB * 24 * CAP;
     int r = set_smem(kernel, smem);
     if (r) return r;
+    tick(32 + 2 * bin);
     kernel<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(
         nb.d_list + nb.off[bin], cntb, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,
         d_urp, C->col, C->val, ro);
+    tick(32 + 2 * bin + 1);
+    num_timed[bin] = true;
     ++launches;
     return B200_OK;
   };
@@ -1028,6 +1065,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if (!num_smem && !d_gscr)
       B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     const int* lst = nb.d_list + nb.off[NB_BITMAP];
+    tick(32 + 2 * NB_BITMAP);
+    num_timed[NB_BITMAP] = true;
 #define LAUNCH_NUM_BM(SM, RM)                                                                   \
   do {                                                                                          \
     if (SM && (rc = set_smem(k_num_bitmap<BT_BIG, SM, RM>, bm_pref_bytes))) return rc;          \
@@ -1042,6 +1081,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(false, false); else LAUNCH_NUM_BM(false, true);
     }
 #undef LAUNCH_NUM_BM
+    tick(32 + 2 * NB_BITMAP + 1);
     ++launches;
   }
   B200_CUDA(cudaGetLastError());
@@ -1083,6 +1123,17 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     dfree(d_scr_col); dfree(d_scr_val);
   }
   B200_CUDA(cudaEventRecord(c.ev[5], st));
+  unsigned long long h_agg[96] = {0};
+  if (stats && m > 0) {
+    unsigned long long* d_agg = nullptr;
+    B200_CUDA(dalloc(&d_agg, 96));
+    B200_CUDA(cudaMemsetAsync(d_agg, 0, 96 * sizeof(unsigned long long), st));
+    const int grid = std::min((m + 255) / 256, c.sm_count * 8);
+    k_bin_aggregate<<<grid, 256, 0, st>>>(d_bin, m, A.rowptr, row_lo, d_flops, nullptr, d_agg);
+    k_bin_aggregate<<<grid, 256, 0, st>>>(d_nbin, m, A.rowptr, row_lo, d_flops, d_cnt, d_agg + 48);
+    B200_CUDA(cudaMemcpyAsync(h_agg, d_agg, sizeof h_agg, cudaMemcpyDeviceToHost, st));
+    dfree(d_agg);
+  }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_bmstore); dfree(d_gscr); dfree(d_work);
   dfree(d_bmindex);
@@ -1105,7 +1156,18 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->nnz_out = nnz_out;
     stats->nnz_unpruned = unpruned;
     stats->launches = launches;
-    for (int b = 0; b < 16; ++b) stats->bins_rows[b] = nb.cnt[b];
+    for (int b = 0; b < 16; ++b) {
+      stats->bins_rows[b] = nb.cnt[b];
+      stats->sym_bin_rows[b] = sb.cnt[b];
+      stats->sym_bin_products[b] = (long long)h_agg[b * 3 + 0];
+      stats->sym_bin_nnzA[b] = (long long)h_agg[b * 3 + 1];
+      stats->num_bin_products[b] = (long long)h_agg[48 + b * 3 + 0];
+      stats->num_bin_nnzA[b] = (long long)h_agg[48 + b * 3 + 1];
+      stats->num_bin_nnzC[b] = (long long)h_agg[48 + b * 3 + 2];
+      float t = 0;
+      if (sym_timed[b]) { cudaEventElapsedTime(&t, c.kev[2 * b], c.kev[2 * b + 1]); stats->ms_sym_bin[b] = t; }
+      if (num_timed[b]) { cudaEventElapsedTime(&t, c.kev[32 + 2 * b], c.kev[32 + 2 * b + 1]); stats->ms_num_bin[b] = t; }
+    }
   }
   return B200_OK;
 }

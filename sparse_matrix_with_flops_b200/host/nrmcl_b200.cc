@@ -1,0 +1,78 @@
+// nrmcl_b200.cc — C++ host driver over the C-ABI, in the shape of the reference's one-main
+// drivers (nrmcl.cc:12-37 for rMCL, perfTests/only-somp.cc:24-37 for SpGEMM timing).  Host code
+// only: every computation goes through include/b200_nlibs.hpp -> libb200spgemm.so.
+//
+//   nrmcl_b200.x rmcl  <rmat|stencil|planted> <size> [maxIters] [eps]
+//   nrmcl_b200.x spmm  <rmat|stencil|planted> <size> [reps]
+//
+// size: R-MAT scale / stencil grid edge / planted-partition vertices (1000-vertex blocks).
+#include <chrono>
+#include <set>
+#include "b200_nlibs.hpp"
+
+using namespace b200::nlibs;
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+static CSR make_input(const char* kind, int size, bool symmetrise) {
+  int rows = 0; long long nnz = 0;
+  int *I = NULL, *J = NULL; double* V = NULL;
+  int rc;
+  if (!strcmp(kind, "rmat")) rc = b200_synth_rmat(size, 16, 12345ull, symmetrise, &rows, &I, &J, &V, &nnz);
+  else if (!strcmp(kind, "stencil")) rc = b200_synth_stencil27(size, size, size, &rows, &I, &J, &V, &nnz);
+  else if (!strcmp(kind, "planted")) rc = b200_synth_planted(size, std::max(1, size / 1000), 16, 2, 12345ull, &rows, &I, &J, &V, &nnz, NULL);
+  else { fprintf(stderr, "unknown input kind %s\n", kind); exit(EXIT_FAILURE); }
+  b200_check(rc, "b200_synth");
+  return CSR(V, J, I, rows, rows, (int)nnz);
+}
+
+int main(int argc, char* argv[]) {
+  if (argc < 4) {
+    fprintf(stderr, "usage: %s rmcl|spmm rmat|stencil|planted size [maxIters|reps] [eps]\n", argv[0]);
+    return 2;
+  }
+  const bool rmcl = !strcmp(argv[1], "rmcl");
+  const int size = atoi(argv[3]);
+  const int count = argc > 4 ? atoi(argv[4]) : 5;   // maxIters default 5 (process_args.h:28)
+  const double eps = argc > 5 ? atof(argv[5]) : 0.0;
+  b200_ensure_init();
+  CSR A = make_input(argv[2], size, rmcl);
+  printf("input %s %d: rows %d nnz %d\n", argv[2], size, A.rows, A.nnz);
+  if (rmcl) {
+    CSR Mgt = A.deepCopy();
+    std::vector<double> hist(std::max(1, count));
+    int iters = 0;
+    double t0 = now_ms();
+    gpuRmclIter(count, Mgt, A, eps, &iters, hist.data());
+    double ms = now_ms() - t0;
+    std::set<int> attractors;
+    for (int i = 0; i < A.rows; ++i) {
+      int best = -1; double bv = 0.0;
+      for (int p = A.rowPtr[i]; p < A.rowPtr[i + 1]; ++p)
+        if (best < 0 || A.values[p] > bv) { best = A.colInd[p]; bv = A.values[p]; }
+      attractors.insert(best);
+    }
+    printf("time pass b200 rmcl total = %lf ms, iters %d, %.3f iter/s, final nnz %d, chaos %.6g, clusters %zu\n",
+           ms, iters, iters / (ms * 1e-3), A.nnz, iters ? hist[iters - 1] : 0.0, attractors.size());
+    Mgt.dispose();
+  } else {
+    const long long products = A.spMMFlops(A);
+    CSR dA = A.toGpuCSR();
+    double best = 1e300;
+    for (int r = 0; r < count + 1; ++r) {   // 1 warm-up + count reps, as perfTests/only-somp.cc does
+      double t0 = now_ms();
+      CSR dC = gpuSpMMWrapper(dA, dA);
+      double ms = now_ms() - t0;
+      if (r) best = std::min(best, ms);
+      dC.deviceDispose();
+    }
+    printf("b200 spmm best %lf ms, products %lld, GFLOPS %.3f\n", best, products, 2.0 * products / best / 1e6);
+    dA.deviceDispose();
+  }
+  A.dispose();
+  b200_finalize();
+  return 0;
+}

@@ -24,7 +24,27 @@ for c in cases:
         print("  spgemm rep%d total %.2f ms (flops %.2f sym %.2f num %.2f other %.2f) P=%d nnzC=%d GF=%.1f algGB/s=%.0f bins=%s" % (
             rep, st["ms_total"], st["ms_flops"], st["ms_symbolic"], st["ms_numeric"], st["ms_other"],
             st["products"], st["nnz_out"], 2 * st["products"] / st["ms_total"] / 1e6, by / st["ms_total"] / 1e6,
-            st["bins_rows"][:5]), flush=True)
+            st["bins_rows"][:6]), flush=True)
+        if rep == 2:
+            for b in range(1, 6):
+                print("    sym bin%d rows %8d P %12d  %8.2f ms | num bin%d rows %8d P %12d nnzC %11d %8.2f ms" % (
+                    b, st["sym_bin_rows"][b], st["sym_bin_products"][b], st["ms_sym_bin"][b],
+                    b, st["bins_rows"][b], st["num_bin_products"][b], st["num_bin_nnzC"][b], st["ms_num_bin"][b]), flush=True)
+    if os.environ.get("DUMP_DIST"):
+        dC = smf.gpuSpMMWrapper(dA, dA)
+        import ctypes as C
+        from sparse_matrix_with_flops_b200 import _lib
+        pre = smf.flops_prefix(dA, dA)
+        rp = C.c_void_p()
+        _lib.load().b200_csr_device_ptrs(dC.handle, C.byref(rp), None, None)
+        import torch
+        # rowptr (int64, device) -> host through a raw cudaMemcpy via torch's cudart
+        out = np.empty(A.rows + 1, dtype=np.int64)
+        torch.cuda.cudart().cudaMemcpy(out.ctypes.data, rp.value, out.nbytes, 2)
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed("gpurun_out/dist_%s.npz" % c, P=np.diff(pre).astype(np.int64), nnzC=np.diff(out).astype(np.int32),
+                            nnzA=np.diff(A.rowPtr).astype(np.int32))
+        dC.deviceDispose()
     if c != "rmat20d":
         dM = dA
         for it in range(6):
