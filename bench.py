@@ -95,9 +95,11 @@ def host_flops_prefix(A):
 
 # ---- CPU baseline (checker libraries; never on the GPU path) --------------------------------
 
-def row_sample(A, q, r=0):
-    """Rows r, r+q, r+2q, ... of A as a CSR over the same columns."""
-    rows = np.arange(r, A.rows, q, dtype=np.int64)
+def row_sample(A, q):
+    """A pseudo-random 1/q of the rows of A (Fibonacci hash of the row id; a plain stride would
+    over-sample R-MAT's hubs, whose ids end in zero bits) as a CSR over the same columns."""
+    ids = np.arange(A.rows, dtype=np.uint64)
+    rows = np.nonzero(((ids * np.uint64(2654435761)) % np.uint64(1 << 32)) < np.uint64((1 << 32) // q))[0].astype(np.int64)
     starts, ends = A.rowPtr[rows].astype(np.int64), A.rowPtr[rows + 1].astype(np.int64)
     lens = ends - starts
     I = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
@@ -108,21 +110,26 @@ def row_sample(A, q, r=0):
 class CpuArm:
     """flops_omp_CSR_SpMM of the reference (kind 'reference') or the oracle port (kind 'port')."""
 
-    def __init__(self, A, target_products=2.5e9):
+    def __init__(self, A, target_products=1.5e9):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as ol
         self.ol = ol
         self.A = A
         prefix = host_flops_prefix(A)
         P = int(prefix[-1])
-        self.q = max(1, int(round(P / target_products)))
-        self.I, self.J, self.V, self.m = row_sample(A, self.q)
         rowlen = np.diff(A.rowPtr).astype(np.int64)
-        self.products = int(rowlen[self.J].sum())
+        self.q = max(1, int(np.ceil(P / target_products)))
+        while True:
+            # nnz(C) <= products must fit the reference's `int` CSR (nlibs/CSR.h:38)
+            self.I, self.J, self.V, self.m = row_sample(A, self.q)
+            self.products = int(rowlen[self.J].sum())
+            if self.products <= 2_000_000_000:
+                break
+            self.q += 1
         self.kind = "reference" if os.path.exists(ol.REF_SO) else "port"
         self.cores = os.cpu_count()
-        self.sample = ("rows 0,%d,%d,... of A (%d rows, %d of %d products) x full B" %
-                       (self.q, 2 * self.q, self.m, self.products, P))
+        self.sample = ("hashed 1/%d row sample of A (%d rows, %d of %d products) x full B" %
+                       (self.q, self.m, self.products, P))
 
     def step_ms(self):
         A, ol = self.A, self.ol
@@ -180,49 +187,57 @@ def run_reference(args):
 # ---- clocks ------------------------------------------------------------------------------------
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, through NVML in this process (a
+    background thread; an `nvidia-smi -lms` child proved to stall kernel launches by ~100 ms per
+    query on this driver, so it is not used)."""
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period_s=0.1):
+        import threading
+        self.samples, self.reasons, self.err = [], set(), None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # no NVML: report it, do not fail the bench
+            self.err = repr(e)
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw))
+                for bit, nm in ((self.HW_SLOWDOWN, "hw_slowdown"), (self.SW_THERMAL, "sw_thermal_slowdown"),
+                                (self.HW_THERMAL, "hw_thermal_slowdown"), (self.SW_POWER_CAP, "sw_power_cap")):
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception as e:
+                self.err = repr(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.err and not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(x[0] for x in self.samples), "sm_max_mhz": self.max_sm,
+                "power_w_max": max(x[1] for x in self.samples), "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------

@@ -56,6 +56,90 @@ __global__ void k_row_argmax(const int64_t* __restrict__ rp, const int* __restri
   lab[i] = best;
 }
 
+// ---- staged host <-> device copies ------------------------------------------------------------
+// The reference's containers are plain malloc() blocks (nlibs/CSR.h:323-327), i.e. pageable
+// memory; a direct cudaMemcpy to or from it runs at a few GB/s (driver-side staging on one
+// thread plus first-touch page faults).  Instead: DMA through two pinned buffers on a second
+// stream while all host cores copy the previous chunk between the pinned buffer and the user's
+// block (which also first-touches a fresh malloc block in parallel).
+constexpr size_t PIN_BYTES = 64u << 20;
+
+int ensure_staging() {
+  Ctx& c = ctx();
+  if (c.pin[0]) return B200_OK;
+  B200_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    B200_CUDA(cudaHostAlloc(&c.pin[k], PIN_BYTES, cudaHostAllocDefault));
+    B200_CUDA(cudaEventCreateWithFlags(&c.pin_ev[k], cudaEventDisableTiming));
+  }
+  B200_CUDA(cudaEventCreateWithFlags(&c.xfer_ev, cudaEventDisableTiming));
+  return B200_OK;
+}
+
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+  const size_t piece = 1u << 20;
+  const long long pieces = (long long)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+  for (long long t = 0; t < pieces; ++t) {
+    const size_t off = (size_t)t * piece;
+    memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
+  }
+}
+
+// device -> host block; everything queued on the library stream before the call is waited for
+int d2h_staged(void* dst, const void* src, size_t bytes) {
+  Ctx& c = ctx();
+  if (!bytes) return B200_OK;
+  if (bytes < (4u << 20)) {
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return B200_OK;
+  }
+  int rc = ensure_staging();
+  if (rc) return rc;
+  B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));
+  B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+  const size_t nchunks = (bytes + PIN_BYTES - 1) / PIN_BYTES;
+  for (size_t k = 0; k <= nchunks; ++k) {
+    if (k < nchunks) {
+      const size_t off = k * PIN_BYTES, len = std::min(PIN_BYTES, bytes - off);
+      B200_CUDA(cudaMemcpyAsync(c.pin[k & 1], (const char*)src + off, len, cudaMemcpyDeviceToHost, c.copy_stream));
+      B200_CUDA(cudaEventRecord(c.pin_ev[k & 1], c.copy_stream));
+    }
+    if (k > 0) {
+      const size_t off = (k - 1) * PIN_BYTES, len = std::min(PIN_BYTES, bytes - off);
+      B200_CUDA(cudaEventSynchronize(c.pin_ev[(k - 1) & 1]));
+      parallel_copy((char*)dst + off, c.pin[(k - 1) & 1], len);
+    }
+  }
+  return B200_OK;
+}
+
+// host block -> device; returns after the last DMA has been queued AND completed
+int h2d_staged(void* dst, const void* src, size_t bytes) {
+  Ctx& c = ctx();
+  if (!bytes) return B200_OK;
+  if (bytes < (4u << 20)) {
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+    return B200_OK;
+  }
+  int rc = ensure_staging();
+  if (rc) return rc;
+  B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));   // dst was allocated on the library stream
+  B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+  const size_t nchunks = (bytes + PIN_BYTES - 1) / PIN_BYTES;
+  for (size_t k = 0; k < nchunks; ++k) {
+    const size_t off = k * PIN_BYTES, len = std::min(PIN_BYTES, bytes - off);
+    if (k >= 2) B200_CUDA(cudaEventSynchronize(c.pin_ev[k & 1]));  // buffer free again
+    parallel_copy(c.pin[k & 1], (const char*)src + off, len);
+    B200_CUDA(cudaMemcpyAsync((char*)dst + off, c.pin[k & 1], len, cudaMemcpyHostToDevice, c.copy_stream));
+    B200_CUDA(cudaEventRecord(c.pin_ev[k & 1], c.copy_stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(c.copy_stream));
+  return B200_OK;
+}
+
 int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V, int* nnz) {
   Ctx& c = ctx();
   if (lo < 0 || hi > d.rows || lo > hi) { set_error("row range out of bounds"); return B200_ERR_BAD_ARG; }
@@ -77,12 +161,13 @@ int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V,
   B200_CUDA(dalloc(&d32, (size_t)m + 1));
   k_i64_to_i32_rebased<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c.stream>>>(d.rowptr + lo, d32, m + 1);
   B200_CUDA(cudaMemcpyAsync(hi32, d32, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  if (cnt) {
-    B200_CUDA(cudaMemcpyAsync(hj, d.col + ends[0], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    B200_CUDA(cudaMemcpyAsync(hv, d.val + ends[0], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  }
   dfree(d32);
   B200_CUDA(cudaStreamSynchronize(c.stream));
+  if (cnt) {
+    int rc = d2h_staged(hj, d.col + ends[0], (size_t)cnt * sizeof(int));
+    if (!rc) rc = d2h_staged(hv, d.val + ends[0], (size_t)cnt * sizeof(double));
+    if (rc) { free(hi32); free(hj); free(hv); return rc; }
+  }
   *I = hi32; *J = hj; *V = hv; *nnz = (int)cnt;
   return B200_OK;
 }
@@ -102,12 +187,13 @@ int upload(const int* I, const int* J, const double* V, int rows, int cols, int 
   B200_CUDA(dalloc(&d.val, (size_t)nnz));
   B200_CUDA(cudaMemcpyAsync(tmp, I, ((size_t)rows + 1) * sizeof(int), cudaMemcpyHostToDevice, c.stream));
   k_i32_to_i64<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, c.stream>>>(tmp, d.rowptr, rows + 1);
-  if (nnz) {
-    B200_CUDA(cudaMemcpyAsync(d.col, J, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-    B200_CUDA(cudaMemcpyAsync(d.val, V, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-  }
   dfree(tmp);
   B200_CUDA(cudaStreamSynchronize(c.stream));
+  if (nnz) {
+    int rc = h2d_staged(d.col, J, (size_t)nnz * sizeof(int));
+    if (!rc) rc = h2d_staged(d.val, V, (size_t)nnz * sizeof(double));
+    if (rc) { dfree(d.rowptr); dfree(d.col); dfree(d.val); return rc; }
+  }
   *out = d;
   return B200_OK;
 }
@@ -169,6 +255,12 @@ int b200_finalize(void) {
   for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
+  if (c.pin[0]) {
+    for (int k = 0; k < 2; ++k) { cudaFreeHost(c.pin[k]); c.pin[k] = nullptr; cudaEventDestroy(c.pin_ev[k]); }
+    cudaEventDestroy(c.xfer_ev);
+    cudaStreamDestroy(c.copy_stream);
+    c.copy_stream = nullptr;
+  }
   c.ready = false;
   return B200_OK;
 }

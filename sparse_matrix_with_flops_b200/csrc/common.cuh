@@ -37,6 +37,12 @@ struct Ctx {
   cudaEvent_t ev[8] = {};
   cudaEvent_t kev[64] = {};  // per-kernel brackets: [2*b], [2*b+1] symbolic bin b; 32+ numeric
   char name[128] = {0};
+  // host <-> device staging for the host-buffer entry points (capi.cu): two pinned buffers on a
+  // second stream, so the DMA of chunk k overlaps the host-side copy of chunk k-1
+  cudaStream_t copy_stream = nullptr;
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t pin_ev[2] = {};
+  cudaEvent_t xfer_ev = nullptr;
 };
 Ctx& ctx();
 

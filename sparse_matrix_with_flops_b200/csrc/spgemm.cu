@@ -56,21 +56,25 @@ constexpr int NB_W1K = 3;
 constexpr int NB_W2K = 4;
 constexpr int NB_BITMAP = 5;
 
-__host__ __device__ inline int sym_bin_of(long long P, int annz) {
+// `big_from`: rows above this size go to the bitmap bin.  When the column bitmap of B fits in
+// shared memory it is the cheapest accumulator index for every row past the small warp tables
+// (its per-row cost is O(n/64) words to clear), so the cut is low (P > 512, nnz(C_i) > 256);
+// otherwise the larger warp tables take the rows up to 8192 products / 2048 entries.
+__host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_from) {
   if (P == 0 || annz <= 1) return SB_NONE;
   if (P <= 128) return SB_W256;
   if (P <= 512) return SB_W1K;
+  if (P > big_from) return SB_BITMAP;
   if (P <= 2048) return SB_W4K;
-  if (P <= 8192) return SB_W16K;
-  return SB_BITMAP;
+  return SB_W16K;
 }
-__host__ __device__ inline int num_bin_of(int cnt) {
+__host__ __device__ inline int num_bin_of(int cnt, int big_from) {
   if (cnt == 0) return NB_NONE;
   if (cnt <= 64) return NB_W64;
   if (cnt <= 256) return NB_W256;
+  if (cnt > big_from) return NB_BITMAP;
   if (cnt <= 1024) return NB_W1K;
-  if (cnt <= 2048) return NB_W2K;
-  return NB_BITMAP;
+  return NB_W2K;
 }
 
 // Fibonacci hashing: the slot is the TOP log2(H) bits of c * 2^32/phi.  (Taking low bits of a
@@ -117,6 +121,55 @@ __device__ __forceinline__ int warp_sum_int(int v) {
   return v;
 }
 
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint) -----------------------------
+// The numeric pass of a heavy row keeps three kinds of lines in flight: the row's accumulators
+// (zeroed, then hit by one fp64 RED per product: best kept in L2 until the row is done), the
+// gathered B rows (re-used across rows only when they are hub rows) and pure streams (the
+// column list being written, the stored bitmaps being read).  Measured on R-MAT scale 20:
+// accumulators evict_last + streams evict_first is worth 6 % of the kernel; the kernel is bound
+// by the SM-side fp64 RED issue rate, not by where the line lives (profiles/README.md).
+enum L2Prio { L2_NORMAL = 0, L2_FIRST = 1, L2_LAST = 2 };
+__device__ __forceinline__ unsigned long long l2_policy(int prio) {
+  unsigned long long p;
+  if (prio == L2_LAST) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (prio == L2_FIRST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int ldg_hint(const int* a, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ldg_hint(const double* a, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ ulonglong2 ldg_hint(const ulonglong2* a, unsigned long long pol) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(double* a, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(int* a, int v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(unsigned long long* a, unsigned long long v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_hint(double* a, double v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+// drop a 128-byte line back to normal priority (after the row that owned it is complete)
+__device__ __forceinline__ void l2_demote(const void* a) {
+  asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(a) : "memory");
+}
+// packed per-kernel policy choices (host side: see l2_modes() in run_pipeline)
+struct L2Modes { int acc, ocol, bgather, bmstore, demote; };
+
 // computeThreshold (nlibs/tools/util.cc:4-9) with the reference's operation order and no
 // fused multiply-add: ((0.9*avg) * (1 - (2*(max-avg)))), floor 1e-7, cap at max.
 __device__ __forceinline__ double compute_threshold(double avg, double mx) {
@@ -131,8 +184,9 @@ __device__ __forceinline__ double compute_threshold(double avg, double mx) {
 // one thread per row; also emits the symbolic bin and, for rows that need no hashing, nnz(C_i).
 __global__ void __launch_bounds__(256)
 k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
-            const int64_t* __restrict__ Brp, int row_lo, int m, long long* __restrict__ flops,
-            unsigned char* __restrict__ sbin, int* __restrict__ rownnz) {
+            const int64_t* __restrict__ Brp, int row_lo, int m, long long big_from,
+            long long* __restrict__ flops, unsigned char* __restrict__ sbin,
+            int* __restrict__ rownnz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
@@ -142,15 +196,15 @@ k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
     f += __ldg(Brp + j + 1) - __ldg(Brp + j);
   }
   flops[i] = f;
-  int b = sym_bin_of(f, (int)(a1 - a0));
+  int b = sym_bin_of(f, (int)(a1 - a0), big_from);
   sbin[i] = (unsigned char)b;
   if (b == SB_NONE) rownnz[i] = (int)f;  // 0, or the length of the single B row
 }
 
 __global__ void __launch_bounds__(256)
-k_num_bins(const int* __restrict__ rownnz, int m, unsigned char* __restrict__ nbin) {
+k_num_bins(const int* __restrict__ rownnz, int m, int big_from, unsigned char* __restrict__ nbin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) nbin[i] = (unsigned char)num_bin_of(rownnz[i]);
+  if (i < m) nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from);
 }
 
 // histogram of bin ids (<= 16 bins)
@@ -498,55 +552,220 @@ __device__ __forceinline__ double block_max_d(double v, double* s_redd) {
   return t;
 }
 
-// Walk the products of one A row with the whole CTA: each warp takes chunks of 32 A entries,
-// loads (col, val, B row bounds) lane-parallel, then spreads its lanes over each B row.
-template <typename F>
-__device__ __forceinline__ void cta_for_each_product(int64_t a0, int64_t a1,
-                                                     const int* __restrict__ Acol,
-                                                     const double* __restrict__ Aval,
-                                                     const int64_t* __restrict__ Brp,
-                                                     const int* __restrict__ Bcol,
-                                                     const double* __restrict__ Bval, F f) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int64_t base = a0 + (int64_t)warp * 32; base < a1; base += (int64_t)nwarps * 32) {
-    const int64_t p = base + lane;
-    long long bs = 0, be = 0;
-    double av = 0.0;
-    if (p < a1) {
-      int j = __ldg(Acol + p);
-      if (Aval) av = __ldg(Aval + p);
-      bs = __ldg(Brp + j);
-      be = __ldg(Brp + j + 1);
+// exclusive scan of one 64-bit value per thread; s_red64 needs BT/32 + 1 slots.  The warp
+// totals are scanned by warp 0 with shuffles (not by every thread with a 32-step loop).
+__device__ __forceinline__ long long shfl_up64(long long v, int o) {
+  const int lo = __shfl_up_sync(FULL, (int)(v & 0xffffffffLL), o);
+  const int hi = __shfl_up_sync(FULL, (int)(v >> 32), o);
+  return ((long long)hi << 32) | (unsigned)lo;
+}
+template <int BT>
+__device__ __forceinline__ long long block_excl_scan64(long long v, long long* s_red64,
+                                                       long long* total) {
+  static_assert(BT / 32 <= 32, "one warp scans the warp totals");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long y = shfl_up64(inc, o);
+    if (lane >= o) inc += y;
+  }
+  __syncthreads();
+  if (lane == 31) s_red64[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const long long t = (lane < BT / 32) ? s_red64[lane] : 0;
+    long long ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = shfl_up64(ti, o);
+      if (lane >= o) ti += y;
     }
-    const int nn = (int)min((int64_t)32, a1 - base);
-    for (int t = 0; t < nn; ++t) {
-      const long long s = shfl64(bs, t), e = shfl64(be, t);
-      const double a = shfld(av, t);
-      for (long long q = s + lane; q < e; q += 32) {
-        const int c = __ldg(Bcol + q);
-        f(c, a, q);
-      }
+    if (lane < BT / 32) s_red64[lane] = ti - t;
+    if (lane == 31) s_red64[BT / 32] = ti;
+  }
+  __syncthreads();
+  *total = s_red64[BT / 32];
+  return s_red64[warp] + inc - v;
+}
+
+// Shared-memory work area of the flat product walk: one slot per A entry of the current batch.
+template <int BT>
+struct WalkSmem {
+  long long end[BT];   // inclusive end of the entry's products in the batch's flat index space
+  long long base[BT];  // B-row start minus the entry's first flat index: q = base + x
+  double a[BT];        // A value of the entry
+  long long red[BT / 32 + 2];  // + total, + pad: the bitmap behind this struct is 16-byte aligned
+};
+static_assert(sizeof(WalkSmem<1024>) % 16 == 0, "bitmap must stay 16-byte aligned");
+
+// Walk the products of one A row with the whole CTA, FLAT: the products of a batch of up to BT
+// A entries are numbered 0..T-1 in (A entry, position in its B row) order.  Every thread is busy
+// whatever the shape of the row — 5 A entries with B rows of 1500 columns (the typical heavy
+// R-MAT row) or 30 000 entries of mixed lengths — and consecutive lanes read consecutive
+// elements of a B row.  Three steps:
+//   walk_prepare   load the batch's A entries, scan their B-row lengths into shared memory;
+//   walk_prefetch  ask L2 for the B-row segments (one line per 32 columns, two per 32 values);
+//                  issued early in a row's life so the DRAM latency of the gather overlaps the
+//                  bitmap / prefix / column-emission phases instead of stalling the products;
+//   walk_run       each warp takes a contiguous slice of the flat index space (a multiple of 32
+//                  long), its lanes consecutive indices; four products are in flight per thread.
+template <int BT, bool WITH_VAL>
+__device__ __forceinline__ long long walk_prepare(int64_t b0, int nb, const int* __restrict__ Acol,
+                                                  const double* __restrict__ Aval,
+                                                  const int64_t* __restrict__ Brp,
+                                                  WalkSmem<BT>& ws) {
+  long long len = 0, bs = 0;
+  double a = 0.0;
+  if ((int)threadIdx.x < nb) {
+    const int j = __ldg(Acol + b0 + threadIdx.x);
+    if (WITH_VAL) a = __ldg(Aval + b0 + threadIdx.x);
+    bs = __ldg(Brp + j);
+    len = __ldg(Brp + j + 1) - bs;
+  }
+  long long total;
+  const long long ex = block_excl_scan64<BT>(len, ws.red, &total);
+  ws.end[threadIdx.x] = ((int)threadIdx.x < nb) ? ex + len : total;  // pad: never matched
+  ws.base[threadIdx.x] = bs - ex;
+  ws.a[threadIdx.x] = a;
+  __syncthreads();
+  return total;
+}
+
+// slice of the flat index space owned by this warp, and the entry holding its first index
+template <int BT>
+__device__ __forceinline__ bool walk_slice(const WalkSmem<BT>& ws, int nb, long long total,
+                                           long long* xb, long long* xe, int* e0) {
+  constexpr int NWARPS = BT / 32;
+  const int warp = threadIdx.x >> 5;
+  const long long per_warp = (((total + NWARPS - 1) / NWARPS) + 31) & ~31LL;
+  *xb = (long long)warp * per_warp;
+  *xe = min(total, *xb + per_warp);
+  if (*xb >= *xe) return false;
+  int lo = 0, hi = nb - 1;  // xb < total guarantees an answer
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (*xb < ws.end[mid]) hi = mid; else lo = mid + 1;
+  }
+  *e0 = lo;
+  return true;
+}
+
+template <int BT, bool WITH_VAL>
+__device__ __forceinline__ void walk_prefetch(const WalkSmem<BT>& ws, int nb, long long total,
+                                              const int* __restrict__ Bcol,
+                                              const double* __restrict__ Bval) {
+  long long xb, xe;
+  int e;
+  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e)) return;
+  const int lane = threadIdx.x & 31;
+  // lane l looks after the 32-index step starting at xb + 32*l (then +1024, ...): one line of
+  // columns and two of values per step, addressed by the step's first element
+  for (long long x = xb + 32LL * lane; x < xe; x += 1024) {
+    while (x >= ws.end[e]) ++e;
+    const long long q = ws.base[e] + x;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(Bcol + q));
+    if (WITH_VAL) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Bval + q));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Bval + q + 16));
     }
   }
 }
 
+template <int BT, bool WITH_VAL, typename F>
+__device__ __forceinline__ void walk_run(const WalkSmem<BT>& ws, int nb, long long total,
+                                         const int* __restrict__ Bcol,
+                                         const double* __restrict__ Bval, unsigned long long bpol,
+                                         F f) {
+  long long xb, xe;
+  int e;
+  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e)) return;
+  const int lane = threadIdx.x & 31;
+  long long x = xb + lane;
+  for (; x + 96 < xe; x += 128) {
+    long long q[4];
+    double av[4];
+    while (x >= ws.end[e]) ++e;
+    if (x + 96 < ws.end[e]) {  // all four in the same B row (the common case)
+      const long long base = ws.base[e] + x;
+      const double a = ws.a[e];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { q[u] = base + 32 * u; av[u] = a; }
+    } else {
+      int eu = e;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        while (x + 32 * u >= ws.end[eu]) ++eu;
+        q[u] = ws.base[eu] + x + 32 * u;
+        av[u] = ws.a[eu];
+      }
+    }
+    int col[4];
+    double bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      col[u] = ldg_hint(Bcol + q[u], bpol);
+      if (WITH_VAL) bv[u] = ldg_hint(Bval + q[u], bpol);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) f(col[u], WITH_VAL ? __dmul_rn(av[u], bv[u]) : 0.0);
+  }
+  for (; x < xe; x += 32) {
+    while (x >= ws.end[e]) ++e;
+    const long long q = ws.base[e] + x;
+    const int col = ldg_hint(Bcol + q, bpol);
+    f(col, WITH_VAL ? __dmul_rn(ws.a[e], ldg_hint(Bval + q, bpol)) : 0.0);
+  }
+}
+
+// prepare + run over every batch of the row (no early prefetch)
+template <int BT, bool WITH_VAL, typename F>
+__device__ __forceinline__ void cta_products_flat(int64_t a0, int64_t a1,
+                                                  const int* __restrict__ Acol,
+                                                  const double* __restrict__ Aval,
+                                                  const int64_t* __restrict__ Brp,
+                                                  const int* __restrict__ Bcol,
+                                                  const double* __restrict__ Bval,
+                                                  WalkSmem<BT>& ws, unsigned long long bpol,
+                                                  F f) {
+  for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+    const int nb = (int)min((int64_t)BT, a1 - b0);
+    const long long total = walk_prepare<BT, WITH_VAL>(b0, nb, Acol, Aval, Brp, ws);
+    walk_run<BT, WITH_VAL>(ws, nb, total, Bcol, Bval, bpol, f);
+    __syncthreads();
+  }
+}
+
+// set bit c of a shared/global bitmap; the plain read first turns most of the work of a row
+// with many repeated columns into loads (an atomic OR only for a bit not seen yet)
+__device__ __forceinline__ void bitmap_set(unsigned* bm32, int c) {
+  const unsigned bit = 1u << (c & 31);
+  unsigned* w = bm32 + (c >> 5);
+  if (!(*(volatile unsigned*)w & bit)) atomicOr(w, bit);
+}
+
 // ------------------------------------------------------------------------------------------
-// symbolic for large rows: CTA per row (persistent, dynamic row fetch), column bitmap of
-// nw64 64-bit words either in shared memory (SMEM_BM) or in a per-CTA HBM scratch.  The
-// bitmap is stored to `bm_store` (per listed row, nw64 words) when bm_store != nullptr.
+// symbolic for large rows: CTA per row (persistent, dynamic row fetch, heaviest rows first),
+// column bitmap of nw64 64-bit words either in shared memory (SMEM_BM) or in a per-CTA HBM
+// scratch.  The bitmaps of the first `store_rows` listed rows are kept in `bm_store` (slot =
+// list position, recorded in bm_slot[row]) for the numeric pass; the others are rebuilt there.
 template <int BT, bool SMEM_BM>
 __global__ void __launch_bounds__(BT, 1)
 k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
              const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
-             const int64_t* __restrict__ Brp, const int* __restrict__ Bcol, int nw64,
+             const int64_t* __restrict__ Brp, const int* __restrict__ Bcol,
+             const long long* __restrict__ flops, int nw64,
              unsigned long long* __restrict__ gscratch, unsigned long long* __restrict__ bm_store,
-             int* __restrict__ rownnz, int* __restrict__ work_counter) {
+             int store_rows, int* __restrict__ bm_slot, int* __restrict__ rownnz,
+             int* __restrict__ work_counter, L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
   __shared__ int s_idx;
-  unsigned long long* bm =
-      SMEM_BM ? (unsigned long long*)smem_raw : gscratch + (size_t)blockIdx.x * nw64;
+  WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
+  unsigned long long* bm = SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
+                                   : gscratch + (size_t)blockIdx.x * nw64;
   unsigned* bm32 = (unsigned*)bm;
+  const unsigned long long pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
   for (int w = threadIdx.x; w < nw64; w += BT) bm[w] = 0ull;
   while (true) {
     __syncthreads();
@@ -556,105 +775,188 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
     if (idx >= count) break;
     const int i = list[idx];
     const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
-    cta_for_each_product(a0, a1, Acol, (const double*)nullptr, Brp, Bcol, (const double*)nullptr,
-                         [&](int c, double, long long) {
-                           atomicOr(&bm32[c >> 5], 1u << (c & 31));
-                         });
-    __syncthreads();
+    cta_products_flat<BT, false>(a0, a1, Acol, (const double*)nullptr, Brp, Bcol,
+                                 (const double*)nullptr, ws, pol_b,
+                                 [&](int c, double) { bitmap_set(bm32, c); });
     int cnt = 0;
-    unsigned long long* dst = bm_store ? bm_store + (size_t)idx * nw64 : nullptr;
+    unsigned long long* dst = (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 : nullptr;
     for (int w = threadIdx.x; w < nw64; w += BT) {
       const unsigned long long x = bm[w];
       cnt += __popcll(x);
-      if (dst) dst[w] = x;
+      if (dst) stg_hint(dst + w, x, pol_bm);
       bm[w] = 0ull;
     }
     cnt = block_sum_int<BT>(cnt, s_red);
-    if (threadIdx.x == 0) rownnz[i] = cnt;
+    if (threadIdx.x == 0) {
+      rownnz[i] = cnt;
+      bm_slot[i] = dst ? idx : -1;
+    }
   }
 }
 
 // numeric for large rows: rank(col) = prefix[col/64] + popc(bitmap word below col); products
 // are reduced with fp64 RED into `acc` (the row's final slice of C.val for SpGEMM, a per-CTA
 // scratch for rMCL, where the epilogue then runs over the scratch).
-// bm_index[idx] >= 0: the row's bitmap was stored by the symbolic pass at that slot;
+// bm_slot[row] >= 0: the row's bitmap was stored by the symbolic pass at that slot;
 // < 0: rebuild it here.
 template <int BT, bool SMEM_BM, bool RMCL>
 __global__ void __launch_bounds__(BT, 1)
 k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
              const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
              const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
-             const int* __restrict__ Bcol, const double* __restrict__ Bval, int nw64,
+             const int* __restrict__ Bcol, const double* __restrict__ Bval,
+             const long long* __restrict__ flops, int nw64,
              unsigned long long* __restrict__ gscratch, const unsigned long long* __restrict__ bm_store,
-             const int* __restrict__ bm_index, const int64_t* __restrict__ Crp,
+             const int* __restrict__ bm_slot, const int64_t* __restrict__ Crp,
              int* __restrict__ Ccol, double* __restrict__ Cval, int* __restrict__ scr_col,
              double* __restrict__ scr_val, long long scr_stride, RmclOut ro,
-             int* __restrict__ work_counter) {
+             int* __restrict__ work_counter, unsigned long long* __restrict__ prof,
+             L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
   __shared__ double s_redd[BT / 32];
+  // developer diagnostics (B200_PROF=1): cycles per phase, summed over this CTA's rows
+  long long pc[5] = {0, 0, 0, 0, 0};
+  long long tprev = 0;
+  auto lap = [&](int k) {
+    if (prof && threadIdx.x == 0) { const long long t = clock64(); pc[k] += t - tprev; tprev = t; }
+  };
   __shared__ int s_idx;
   __shared__ unsigned long long s_off;
-  // bitmap words then 32-bit exclusive popcount prefix per word
+  // walk area, then bitmap words, then 32-bit exclusive popcount prefix per word
+  WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm =
-      SMEM_BM ? (unsigned long long*)smem_raw
+      SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
               : gscratch + (size_t)blockIdx.x * ((size_t)nw64 + ((size_t)nw64 + 1) / 2);
   unsigned* pref = (unsigned*)(bm + nw64);
   unsigned* bm32 = (unsigned*)bm;
-  const int chunk = (nw64 + BT - 1) / BT;  // contiguous words per thread
+  const unsigned long long pol_acc = l2_policy(l2.acc), pol_ocol = l2_policy(l2.ocol),
+                           pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) s_idx = atomicAdd(work_counter, 1);
     __syncthreads();
     const int idx = s_idx;
     if (idx >= count) break;
+    if (prof && threadIdx.x == 0) tprev = clock64();
     const int i = list[idx];
     const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
-    const int slotno = bm_index ? bm_index[idx] : -1;
+    const int slotno = bm_slot[i];
+    // Stored bitmap: the walk area is free until the products, so the first batch of A entries
+    // is prepared now and its B-row segments are requested from L2 ahead of time.
+    const int nb0 = (int)min((int64_t)BT, a1 - a0);
+    long long total0 = 0;
+    const bool early = slotno >= 0 && nb0 > 0;
+    if (early) {
+      total0 = walk_prepare<BT, true>(a0, nb0, Acol, Aval, Brp, ws);
+      walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval);
+    }
     if (slotno >= 0) {
-      const unsigned long long* src = bm_store + (size_t)slotno * nw64;
-      for (int w = threadIdx.x; w < nw64; w += BT) bm[w] = src[w];
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bm_store + (size_t)slotno * nw64);
+      ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(bm);
+      for (int w = threadIdx.x; w < (nw64 >> 1); w += BT) dst2[w] = ldg_hint(src + w, pol_bm);
     } else {
       for (int w = threadIdx.x; w < nw64; w += BT) bm[w] = 0ull;
-      __syncthreads();
-      cta_for_each_product(a0, a1, Acol, (const double*)nullptr, Brp, Bcol,
-                           (const double*)nullptr, [&](int c, double, long long) {
-                             atomicOr(&bm32[c >> 5], 1u << (c & 31));
-                           });
+      cta_products_flat<BT, false>(a0, a1, Acol, (const double*)nullptr, Brp, Bcol,
+                                   (const double*)nullptr, ws, pol_b,
+                                   [&](int c, double) { bitmap_set(bm32, c); });
     }
     __syncthreads();
-    // popcount prefix: thread t owns words [t*chunk, (t+1)*chunk)
-    const int w0 = threadIdx.x * chunk, w1 = min(nw64, w0 + chunk);
-    int local = 0;
-    for (int w = w0; w < w1; ++w) local += __popcll(bm[w]);
-    int total;
-    int run = block_excl_scan<BT>(local, s_red, &total);
-    for (int w = w0; w < w1; ++w) { pref[w] = (unsigned)run; run += __popcll(bm[w]); }
-    const int cnt = total;
+    lap(0);
+    // popcount prefix.  Warp wp owns a contiguous run of wpw words and walks it 32 words at a
+    // time (lane = word: conflict-free shared-memory access), scanning the popcounts with
+    // shuffles; the warp totals are then scanned across the CTA and added back.
+    constexpr int NW = BT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpw = (((nw64 + NW - 1) / NW) + 31) & ~31;
+    const int wbeg = warp * wpw, wend = min(nw64, wbeg + wpw);
+    {
+      int run = 0;
+      for (int w = wbeg + lane; w < wbeg + wpw; w += 32) {
+        const int c = (w < wend) ? __popcll(bm[w]) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += y;
+        }
+        if (w < wend) pref[w] = (unsigned)(run + inc - c);
+        run += __shfl_sync(FULL, inc, 31);
+      }
+      __syncthreads();
+      if (lane == 0) s_red[warp] = run;
+      __syncthreads();
+    }
+    int cnt = 0, wbase = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int x = s_red[k];
+      if (k < warp) wbase += x;
+      cnt += x;
+    }
+    for (int w = wbeg + lane; w < wend; w += 32) pref[w] += (unsigned)wbase;
+    __syncthreads();
+    lap(1);
     double* acc = RMCL ? scr_val + (size_t)blockIdx.x * scr_stride : Cval + Crp[i];
     int* ocol = RMCL ? scr_col + (size_t)blockIdx.x * scr_stride : Ccol + Crp[i];
-    for (int k = threadIdx.x; k < cnt; k += BT) acc[k] = 0.0;
-    __syncthreads();
-    // columns in ascending order straight from the bitmap
+    // The accumulators zeroed, and the columns in ascending order straight from the bitmap.
+    // Groups of 32 words are dealt round-robin to the warps (the dense low-column region of a
+    // power-law row is shared by all of them), lane = word.  A dense word (>= 16 columns) is
+    // expanded by the whole warp — lane l tests bits l and l+32, the position is a popcount —
+    // a sparse word by its own lane, bit by bit.  The positions of a group are consecutive
+    // (pref[]), so either way a store instruction lands in a few adjacent sectors.
+    for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(acc + k, 0.0, pol_acc);
     {
-      int pos = (w0 < nw64) ? (int)pref[w0] : 0;
-      for (int w = w0; w < w1; ++w) {
-        unsigned long long x = bm[w];
+      const int ngroups = (nw64 + 31) >> 5;
+      const unsigned lt = lanemask_lt();
+      for (int g = warp; g < ngroups; g += NW) {
+        const int w = g * 32 + lane;
+        unsigned long long x = (w < nw64) ? bm[w] : 0ull;
+        int pos = (w < nw64) ? (int)pref[w] : 0;
+        const bool is_dense = __popcll(x) >= 16;
+        unsigned dense = __ballot_sync(FULL, is_dense);
+        while (dense) {
+          const int src = __ffs((int)dense) - 1;
+          dense &= dense - 1;
+          const unsigned long long xs = (unsigned long long)shfl64((long long)x, src);
+          const int ps = __shfl_sync(FULL, pos, src);
+          const unsigned lo32 = (unsigned)xs, hi32 = (unsigned)(xs >> 32);
+          const int cb = (g * 32 + src) * 64;
+          if ((lo32 >> lane) & 1u) stg_hint(ocol + ps + __popc(lo32 & lt), cb + lane, pol_ocol);
+          if ((hi32 >> lane) & 1u)
+            stg_hint(ocol + ps + __popc(lo32) + __popc(hi32 & lt), cb + 32 + lane, pol_ocol);
+        }
+        if (is_dense) x = 0ull;
+        const int cb = w * 64;
         while (x) {
           const int b = __ffsll((long long)x) - 1;
           x &= x - 1;
-          ocol[pos++] = w * 64 + b;
+          stg_hint(ocol + pos++, cb + b, pol_ocol);
         }
       }
     }
-    cta_for_each_product(a0, a1, Acol, Aval, Brp, Bcol, Bval, [&](int c, double a, long long q) {
-      const int w = c >> 6;
-      const unsigned long long below = bm[w] & ((1ull << (c & 63)) - 1ull);
-      const int rank = (int)pref[w] + __popcll(below);
-      atomicAdd(acc + rank, __dmul_rn(a, __ldg(Bval + q)));
-    });
+    lap(2);
+    {
+      auto accumulate = [&](int c, double prod) {
+        const int w = c >> 6;
+        const unsigned long long below = bm[w] & ((1ull << (c & 63)) - 1ull);
+        const int rank = (int)pref[w] + __popcll(below);
+        red_add_hint(acc + rank, prod, pol_acc);
+      };
+      __syncthreads();  // acc[] zeroed by every thread before the first RED lands
+      for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+        const int nb = (int)min((int64_t)BT, a1 - b0);
+        const long long total = (early && b0 == a0)
+                                    ? total0
+                                    : walk_prepare<BT, true>(b0, nb, Acol, Aval, Brp, ws);
+        walk_run<BT, true>(ws, nb, total, Bcol, Bval, pol_b, accumulate);
+        __syncthreads();
+      }
+    }
+    if (l2.demote)  // the row is complete: its accumulator lines need no protection any more
+      for (int k = threadIdx.x * 16; k < cnt; k += BT * 16) l2_demote(acc + k);
+    lap(3);
     if (!RMCL) continue;
-    __syncthreads();
     // ---- fused rMCL epilogue over the scratch row (ascending columns)
     double psum = 0.0, pmax = 0.0;
     for (int k = threadIdx.x; k < cnt; k += BT) {
@@ -701,7 +1003,18 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
       if (ch < 0.0) ch = 0.0;
       atomicMax(ro.chaos_bits, (unsigned long long)__double_as_longlong(ch));
     }
+    lap(4);
   }
+  if (prof && threadIdx.x == 0)
+    for (int k = 0; k < 5; ++k) atomicAdd(prof + k, (unsigned long long)pc[k]);
+}
+
+// keys for ordering a bitmap-bin list heaviest first: key[t] = flops[list[t]]
+__global__ void __launch_bounds__(256)
+k_gather_keys(const int* __restrict__ list, int count, const long long* __restrict__ flops,
+              long long* __restrict__ keys) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) keys[t] = flops[list[t]];
 }
 
 // rMCL rows whose product is empty keep nothing
@@ -817,7 +1130,7 @@ int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi
   B200_CUDA(cudaMemsetAsync(d_flops + m, 0, sizeof(long long), c.stream));
   if (m > 0)
     k_row_flops<<<(m + 255) / 256, 256, 0, c.stream>>>(A.rowptr, A.col, B.rowptr, row_lo, m,
-                                                       d_flops, d_bin, d_cnt);
+                                                       8192LL, d_flops, d_bin, d_cnt);
   void* tmp = nullptr;
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flops, (long long*)d_prefix, m + 1, c.stream);
@@ -846,6 +1159,23 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   bool sym_timed[16] = {false}, num_timed[16] = {false};
   auto tick = [&](int slot) { if (stats) cudaEventRecord(c.kev[slot], st); };
 
+  // large rows use a column bitmap of nw64 words of 64 columns; where it lives decides the
+  // bin cut points (see sym_bin_of)
+  const int nw64 = (((n + 63) / 64) + 1) & ~1;  // even: rows of the bitmap store stay 16-byte aligned
+  const size_t bm_bytes = (size_t)nw64 * 8;
+  const size_t bm_pref_bytes = bm_bytes + (((size_t)nw64 + 1) / 2) * 8;
+  const size_t walk_bytes = sizeof(WalkSmem<BT_BIG>);
+  const size_t smem_cap = c.smem_optin - 1024 - walk_bytes;  // static shared + the walk area
+  const bool sym_smem = bm_bytes <= smem_cap;
+  const bool num_smem = bm_pref_bytes <= smem_cap;
+  // L2 eviction priorities of the bitmap kernels (B200_L2POL=acc,ocol,bgather,bmstore,demote
+  // overrides them: a developer switch for A/B runs)
+  L2Modes l2m = {L2_LAST, L2_FIRST, L2_NORMAL, L2_FIRST, 0};
+  if (const char* e = getenv("B200_L2POL"))
+    sscanf(e, "%d,%d,%d,%d,%d", &l2m.acc, &l2m.ocol, &l2m.bgather, &l2m.bmstore, &l2m.demote);
+  const long long sym_big_from = sym_smem ? 512 : 8192;
+  const int num_big_from = num_smem ? 256 : 2048;
+
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
   unsigned char* d_bin = nullptr;
@@ -856,8 +1186,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(dalloc(&d_cnt, (size_t)m + 1));
   B200_CUDA(dalloc(&d_P, 2));
   if (m > 0) {
-    k_row_flops<<<(m + 255) / 256, 256, 0, st>>>(A.rowptr, A.col, B.rowptr, row_lo, m, d_flops,
-                                                 d_bin, d_cnt);
+    k_row_flops<<<(m + 255) / 256, 256, 0, st>>>(A.rowptr, A.col, B.rowptr, row_lo, m,
+                                                 sym_big_from, d_flops, d_bin, d_cnt);
     ++launches;
   }
   {
@@ -872,6 +1202,28 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   Bins sb;
   int rc = make_bins(d_bin, m, &sb, &launches);
   if (rc) return rc;
+  // heaviest rows first inside a bitmap bin: the persistent CTAs fetch rows dynamically, and a
+  // hub row picked up last would be the tail of the kernel
+  auto order_heavy_first = [&](int* list, int count) -> int {
+    if (count < 2) return B200_OK;
+    long long *k0 = nullptr, *k1 = nullptr;
+    int* l1 = nullptr;
+    B200_CUDA(dalloc(&k0, (size_t)count));
+    B200_CUDA(dalloc(&k1, (size_t)count));
+    B200_CUDA(dalloc(&l1, (size_t)count));
+    k_gather_keys<<<(count + 255) / 256, 256, 0, st>>>(list, count, d_flops, k0);
+    void* tmp = nullptr;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, k0, k1, list, l1, count, 0, 64, st);
+    B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, st));
+    cub::DeviceRadixSort::SortPairsDescending(tmp, tb, k0, k1, list, l1, count, 0, 64, st);
+    B200_CUDA(cudaMemcpyAsync(list, l1, (size_t)count * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    cudaFreeAsync(tmp, st);
+    dfree(k0); dfree(k1); dfree(l1);
+    launches += 2;
+    return B200_OK;
+  };
+  if ((rc = order_heavy_first(sb.d_list + sb.off[SB_BITMAP], sb.cnt[SB_BITMAP]))) return rc;
   B200_CUDA(cudaEventRecord(c.ev[1], st));
 
   // ---- 2. symbolic per bin
@@ -894,40 +1246,39 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8))) return rc;
   if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3))) return rc;
 
-  // large rows: bitmap.  nw64 words of 64 columns.
-  const int nw64 = (n + 63) / 64;
-  const size_t bm_bytes = (size_t)nw64 * 8;
-  const size_t bm_pref_bytes = bm_bytes + (((size_t)nw64 + 1) / 2) * 8;
-  const size_t smem_cap = c.smem_optin - 1024;  // static shared of the kernels
-  const bool sym_smem = bm_bytes <= smem_cap;
-  const bool num_smem = bm_pref_bytes <= smem_cap;
+  // large rows: bitmap
   unsigned long long* d_bmstore = nullptr;  // stored bitmaps of the symbolic bitmap bin
   unsigned long long* d_gscr = nullptr;     // per-CTA bitmap(+prefix) scratch when not in smem
+  int* d_bmslot = nullptr;                  // [m] slot in d_bmstore, or -1
   int* d_work = nullptr;
   B200_CUDA(dalloc(&d_work, 4));
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
+  B200_CUDA(dalloc(&d_bmslot, (size_t)m));
+  B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
   const int nbig = sb.cnt[SB_BITMAP];
   int big_grid = std::min(nbig, c.sm_count);
-  bool store_bitmaps = false;
+  int store_rows = 0;
   if (nbig) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // keep the bitmaps only if they use a modest share of what is free (C itself comes later)
-    store_bitmaps = (double)nbig * (double)bm_bytes < 0.20 * (double)free_b;
-    if (store_bitmaps) B200_CUDA(dalloc(&d_bmstore, (size_t)nbig * nw64));
+    // keep the bitmaps of the heaviest rows while they use a modest share of what is free (C
+    // itself comes later); the rest are rebuilt by the numeric kernel
+    store_rows = (int)std::min<double>((double)nbig, 0.15 * (double)free_b / (double)bm_bytes);
+    if (store_rows) B200_CUDA(dalloc(&d_bmstore, (size_t)store_rows * nw64));
     if (!sym_smem || !num_smem)
       B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     tick(2 * SB_BITMAP);
     sym_timed[SB_BITMAP] = true;
     if (sym_smem) {
-      if ((rc = set_smem(k_sym_bitmap<BT_BIG, true>, bm_bytes))) return rc;
-      k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, bm_bytes, st>>>(
-          sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, nw64,
-          nullptr, d_bmstore, d_cnt, d_work + 0);
+      if ((rc = set_smem(k_sym_bitmap<BT_BIG, true>, walk_bytes + bm_bytes))) return rc;
+      k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, walk_bytes + bm_bytes, st>>>(
+          sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
+          nw64, nullptr, d_bmstore, store_rows, d_bmslot, d_cnt, d_work + 0, l2m);
     } else {
-      k_sym_bitmap<BT_BIG, false><<<big_grid, BT_BIG, 0, st>>>(
-          sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, nw64,
-          d_gscr, d_bmstore, d_cnt, d_work + 0);
+      if ((rc = set_smem(k_sym_bitmap<BT_BIG, false>, walk_bytes))) return rc;
+      k_sym_bitmap<BT_BIG, false><<<big_grid, BT_BIG, walk_bytes, st>>>(
+          sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
+          nw64, d_gscr, d_bmstore, store_rows, d_bmslot, d_cnt, d_work + 0, l2m);
     }
     tick(2 * SB_BITMAP + 1);
     ++launches;
@@ -939,7 +1290,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   unsigned char* d_nbin = nullptr;
   B200_CUDA(dalloc(&d_nbin, (size_t)m));
   if (m > 0) {
-    k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, m, d_nbin);
+    k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, m, num_big_from, d_nbin);
     ++launches;
   }
   B200_CUDA(cudaMemsetAsync(d_cnt + m, 0, sizeof(int), st));
@@ -962,35 +1313,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   rc = make_bins(d_nbin, m, &nb, &launches);  // synchronises the stream
   if (rc) return rc;
   const long long unpruned = h_tot[0];
-
-  // map rows of the numeric bitmap bin to their stored bitmap (or -1)
-  int* d_bmindex = nullptr;
   const int nbig_num = nb.cnt[NB_BITMAP];
-  std::vector<int> h_bmindex;
-  if (nbig_num) {
-    // stored slot = position in the symbolic bitmap list; build inverse on the host (rare,
-    // small lists) — rows not in the symbolic bitmap bin rebuild their bitmap in the kernel.
-    std::vector<int> h_symlist(nbig), h_numlist(nbig_num);
-    if (nbig)
-      B200_CUDA(cudaMemcpyAsync(h_symlist.data(), sb.d_list + sb.off[SB_BITMAP], nbig * sizeof(int),
-                                cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(h_numlist.data(), nb.d_list + nb.off[NB_BITMAP],
-                              nbig_num * sizeof(int), cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-    h_bmindex.assign(nbig_num, -1);
-    if (store_bitmaps && nbig) {
-      std::vector<std::pair<int, int>> inv(nbig);
-      for (int t = 0; t < nbig; ++t) inv[t] = {h_symlist[t], t};
-      std::sort(inv.begin(), inv.end());
-      for (int t = 0; t < nbig_num; ++t) {
-        auto it = std::lower_bound(inv.begin(), inv.end(), std::make_pair(h_numlist[t], -1));
-        if (it != inv.end() && it->first == h_numlist[t]) h_bmindex[t] = it->second;
-      }
-    }
-    B200_CUDA(dalloc(&d_bmindex, (size_t)nbig_num));
-    B200_CUDA(cudaMemcpyAsync(d_bmindex, h_bmindex.data(), nbig_num * sizeof(int),
-                              cudaMemcpyHostToDevice, st));
-  }
+  if ((rc = order_heavy_first(nb.d_list + nb.off[NB_BITMAP], nbig_num))) return rc;
   B200_CUDA(cudaEventRecord(c.ev[3], st));
 
   // ---- 4. outputs
@@ -1065,15 +1389,21 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if (!num_smem && !d_gscr)
       B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     const int* lst = nb.d_list + nb.off[NB_BITMAP];
+    unsigned long long* d_prof = nullptr;
+    if (getenv("B200_PROF")) {
+      B200_CUDA(dalloc(&d_prof, 8));
+      B200_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
+    }
     tick(32 + 2 * NB_BITMAP);
     num_timed[NB_BITMAP] = true;
 #define LAUNCH_NUM_BM(SM, RM)                                                                   \
   do {                                                                                          \
-    if (SM && (rc = set_smem(k_num_bitmap<BT_BIG, SM, RM>, bm_pref_bytes))) return rc;          \
-    k_num_bitmap<BT_BIG, SM, RM><<<grid, BT_BIG, SM ? bm_pref_bytes : 0, st>>>(                 \
-        lst, nbig_num, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, nw64, d_gscr,    \
-        d_bmstore, d_bmindex, d_urp, C->col, C->val, d_scr_col, d_scr_val, scr_stride, ro,      \
-        d_work + 1);                                                                            \
+    const size_t sm_ = walk_bytes + (SM ? bm_pref_bytes : 0);                                   \
+    if ((rc = set_smem(k_num_bitmap<BT_BIG, SM, RM>, sm_))) return rc;                          \
+    k_num_bitmap<BT_BIG, SM, RM><<<grid, BT_BIG, sm_, st>>>(                                    \
+        lst, nbig_num, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, d_flops, nw64,   \
+        d_gscr, d_bmstore, d_bmslot, d_urp, C->col, C->val, d_scr_col, d_scr_val, scr_stride,   \
+        ro, d_work + 1, d_prof, l2m);                                                           \
   } while (0)
     if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
@@ -1083,6 +1413,14 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
 #undef LAUNCH_NUM_BM
     tick(32 + 2 * NB_BITMAP + 1);
     ++launches;
+    if (d_prof) {
+      unsigned long long h[8];
+      B200_CUDA(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[b200 prof] k_num_bitmap Mcycles/CTA: bitmap %.2f prefix %.2f emit %.2f products %.2f epilogue %.2f (grid %d)\n",
+              h[0] / 1e6 / grid, h[1] / 1e6 / grid, h[2] / 1e6 / grid, h[3] / 1e6 / grid, h[4] / 1e6 / grid, grid);
+      dfree(d_prof);
+    }
   }
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaEventRecord(c.ev[4], st));
@@ -1136,7 +1474,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_bmstore); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmindex);
+  dfree(d_bmslot);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {
