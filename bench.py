@@ -35,10 +35,17 @@ import ctypes as C
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
+
+# Host threads.  torchrun exports OMP_NUM_THREADS=1; the CPU legs (the reference's OpenMP SpGEMM)
+# and the library's host-side staging copies are OpenMP code, so give every rank its share of
+# the cores — all of them for the reference arm, which runs on rank 0 alone — before any
+# OpenMP runtime is loaded.
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+_is_ref = "reference" in sys.argv
+os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // (1 if _is_ref else _world)))
+os.environ.setdefault("OMP_PROC_BIND", "false")
 
 import numpy as np
 

@@ -18,6 +18,10 @@ struct DevCSR {
   double* val = nullptr;
   int rows = 0, cols = 0;
   int64_t nnz = 0;
+  // every row has strictly ascending columns (checked at upload, true by construction for an
+  // SpGEMM result, false for an rMCL step in first-touch order): lets the numeric pass cut a B
+  // row at a column boundary with a binary search
+  bool sorted_rows = false;
 };
 
 }  // namespace b200
@@ -93,6 +97,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
 
 // CSR::makeOrdered on the device (spgemm.cu)
 int sort_rows_device(DevCSR* d);
+// sets d->sorted_rows (spgemm.cu)
+int check_sorted_device(DevCSR* d);
 
 // flops prefix on device (spgemm.cu)
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,

@@ -597,7 +597,8 @@ struct WalkSmem {
   double a[BT];        // A value of the entry
   long long red[BT / 32 + 2];  // + total, + pad: the bitmap behind this struct is 16-byte aligned
 };
-static_assert(sizeof(WalkSmem<1024>) % 16 == 0, "bitmap must stay 16-byte aligned");
+static_assert(sizeof(WalkSmem<1024>) % 16 == 0 && sizeof(WalkSmem<512>) % 16 == 0,
+              "bitmap must stay 16-byte aligned");
 
 // Walk the products of one A row with the whole CTA, FLAT: the products of a batch of up to BT
 // A entries are numbered 0..T-1 in (A entry, position in its B row) order.  Every thread is busy
@@ -682,11 +683,27 @@ __device__ __forceinline__ void walk_run(const WalkSmem<BT>& ws, int nb, long lo
   if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e)) return;
   const int lane = threadIdx.x & 31;
   long long x = xb + lane;
+  // eight products in flight while they all lie in one B row (long rows: the common case)
+  for (; x + 224 < xe; x += 256) {
+    while (x >= ws.end[e]) ++e;
+    if (x + 224 >= ws.end[e]) break;
+    const long long base = ws.base[e] + x;
+    const double a = ws.a[e];
+    int col[8];
+    double bv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      col[u] = ldg_hint(Bcol + base + 32 * u, bpol);
+      if (WITH_VAL) bv[u] = ldg_hint(Bval + base + 32 * u, bpol);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f(col[u], WITH_VAL ? __dmul_rn(a, bv[u]) : 0.0);
+  }
   for (; x + 96 < xe; x += 128) {
     long long q[4];
     double av[4];
     while (x >= ws.end[e]) ++e;
-    if (x + 96 < ws.end[e]) {  // all four in the same B row (the common case)
+    if (x + 96 < ws.end[e]) {  // all four in the same B row
       const long long base = ws.base[e] + x;
       const double a = ws.a[e];
 #pragma unroll
@@ -744,6 +761,8 @@ __device__ __forceinline__ void bitmap_set(unsigned* bm32, int c) {
   if (!(*(volatile unsigned*)w & bit)) atomicOr(w, bit);
 }
 
+constexpr int PARTS_MAX = 4;  // column parts of the part-wise numeric kernel
+
 // ------------------------------------------------------------------------------------------
 // symbolic for large rows: CTA per row (persistent, dynamic row fetch, heaviest rows first),
 // column bitmap of nw64 64-bit words either in shared memory (SMEM_BM) or in a per-CTA HBM
@@ -757,7 +776,8 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
              const long long* __restrict__ flops, int nw64,
              unsigned long long* __restrict__ gscratch, unsigned long long* __restrict__ bm_store,
              int store_rows, int* __restrict__ bm_slot, int* __restrict__ rownnz,
-             int* __restrict__ work_counter, L2Modes l2) {
+             int nparts, int wpp, int* __restrict__ partcnt, int* __restrict__ work_counter,
+             L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
   __shared__ int s_idx;
@@ -779,14 +799,29 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
                                  (const double*)nullptr, ws, pol_b,
                                  [&](int c, double) { bitmap_set(bm32, c); });
     int cnt = 0;
+    int pc[PARTS_MAX] = {0, 0, 0, 0};  // columns per column part (see k_num_bitmap_part)
     unsigned long long* dst = (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 : nullptr;
     for (int w = threadIdx.x; w < nw64; w += BT) {
       const unsigned long long x = bm[w];
-      cnt += __popcll(x);
+      const int c = __popcll(x);
+      cnt += c;
+      if (nparts > 1) {
+        const int h = w / wpp;
+#pragma unroll
+        for (int k = 0; k < PARTS_MAX; ++k) pc[k] += (k == h) ? c : 0;
+      }
       if (dst) stg_hint(dst + w, x, pol_bm);
       bm[w] = 0ull;
     }
     cnt = block_sum_int<BT>(cnt, s_red);
+    if (nparts > 1) {
+      for (int k = 0; k < nparts; ++k) {
+        const int t = block_sum_int<BT>(pc[k], s_red);
+        if (threadIdx.x == 0) partcnt[(size_t)i * PARTS_MAX + k] = t;
+      }
+    } else if (partcnt && threadIdx.x == 0) {
+      partcnt[(size_t)i * PARTS_MAX] = cnt;
+    }
     if (threadIdx.x == 0) {
       rownnz[i] = cnt;
       bm_slot[i] = dst ? idx : -1;
@@ -1009,6 +1044,209 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     for (int k = 0; k < 5; ++k) atomicAdd(prof + k, (unsigned long long)pc[k]);
 }
 
+// first position in the sorted run col[lo..hi) whose column is >= key
+__device__ __forceinline__ long long lower_bound_col(const int* __restrict__ col, long long lo,
+                                                     long long hi, int key) {
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (__ldg(col + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// walk_prepare restricted to the columns [c_lo, c_hi) of every B row (rows sorted): the
+// segment of a B row inside the part is found with binary searches, so the products outside
+// the part are never read
+template <int BT>
+__device__ __forceinline__ long long walk_prepare_part(int64_t b0, int nb,
+                                                       const int* __restrict__ Acol,
+                                                       const double* __restrict__ Aval,
+                                                       const int64_t* __restrict__ Brp,
+                                                       const int* __restrict__ Bcol, int c_lo,
+                                                       int c_hi, bool first, bool last,
+                                                       WalkSmem<BT>& ws) {
+  long long len = 0, bs = 0;
+  double a = 0.0;
+  if ((int)threadIdx.x < nb) {
+    const int j = __ldg(Acol + b0 + threadIdx.x);
+    a = __ldg(Aval + b0 + threadIdx.x);
+    long long s = __ldg(Brp + j), e = __ldg(Brp + j + 1);
+    if (!first) s = lower_bound_col(Bcol, s, e, c_lo);
+    if (!last) e = lower_bound_col(Bcol, s, e, c_hi);
+    bs = s;
+    len = e - s;
+  }
+  long long total;
+  const long long ex = block_excl_scan64<BT>(len, ws.red, &total);
+  ws.end[threadIdx.x] = ((int)threadIdx.x < nb) ? ex + len : total;
+  ws.base[threadIdx.x] = bs - ex;
+  ws.a[threadIdx.x] = a;
+  __syncthreads();
+  return total;
+}
+
+// numeric for large rows, PART-WISE (SpGEMM with sorted B rows): the columns of B are cut into
+// nparts parts of wpp bitmap words, a work item is (row, part), handled by a 512-thread CTA with
+// the part's bitmap + popcount prefix in shared memory (<= 100 KB) — so TWO CTAs are resident
+// per SM and the serial phases of one item (ticket, bitmap load, prefix, column emission)
+// overlap the RED-bound product phase of the other.  Item (row, h) writes the slice of the
+// output row that starts partcnt[row][0..h) entries in.
+template <int BT>
+__global__ void __launch_bounds__(BT, 2)
+k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, int row_lo,
+                  const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
+                  const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
+                  const int* __restrict__ Bcol, const double* __restrict__ Bval, int nw64,
+                  const unsigned long long* __restrict__ bm_store,
+                  const int* __restrict__ bm_slot, const int* __restrict__ partcnt,
+                  const int64_t* __restrict__ Crp, int* __restrict__ Ccol,
+                  double* __restrict__ Cval, int* __restrict__ work_counter, L2Modes l2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_red[BT / 32];
+  __shared__ int s_idx;
+  constexpr int NW = BT / 32;
+  WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
+  unsigned long long* bm = (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>));
+  unsigned* pref = (unsigned*)(bm + wpp);
+  unsigned* bm32 = (unsigned*)bm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long pol_acc = l2_policy(l2.acc), pol_ocol = l2_policy(l2.ocol),
+                           pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
+  const int items = count * nparts;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int t = s_idx;
+    if (t >= items) break;
+    const int i = list[t / nparts], h = t % nparts;
+    const int* pc = partcnt + (size_t)i * PARTS_MAX;
+    const int cnt = pc[h];
+    if (cnt == 0) continue;
+    int base = 0;
+    for (int k = 0; k < h; ++k) base += pc[k];
+    const int w_lo = h * wpp, nwp = min(wpp, nw64 - w_lo);
+    const int c_lo = w_lo * 64, c_hi = c_lo + nwp * 64;
+    const bool first = h == 0, last = h == nparts - 1;
+    const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+    const int slotno = bm_slot[i];
+    // first batch of A entries: segments located, B lines requested from L2 ahead of use
+    const int nb0 = (int)min((int64_t)BT, a1 - a0);
+    const long long total0 =
+        walk_prepare_part<BT>(a0, nb0, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
+    walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval);
+    bool batch0_ready = true;
+    // ---- the part's bitmap
+    if (slotno >= 0) {
+      const ulonglong2* src =
+          reinterpret_cast<const ulonglong2*>(bm_store + (size_t)slotno * nw64 + w_lo);
+      ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(bm);
+      for (int w = threadIdx.x; w < (nwp >> 1); w += BT) dst2[w] = ldg_hint(src + w, pol_bm);
+    } else {
+      for (int w = threadIdx.x; w < nwp; w += BT) bm[w] = 0ull;
+      __syncthreads();
+      for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+        const int nb = (int)min((int64_t)BT, a1 - b0);
+        const long long total =
+            (b0 == a0) ? total0
+                       : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, c_lo, c_hi, first,
+                                               last, ws);
+        walk_run<BT, false>(ws, nb, total, Bcol, (const double*)nullptr, pol_b,
+                            [&](int c, double) { bitmap_set(bm32, c - c_lo); });
+        __syncthreads();
+      }
+      batch0_ready = (a1 - a0) <= BT;  // the walk area still holds batch 0 only then
+    }
+    __syncthreads();
+    // ---- popcount prefix (lane = word), warp totals scanned across the CTA
+    const int wpw = (((nwp + NW - 1) / NW) + 31) & ~31;
+    const int wbeg = warp * wpw, wend = min(nwp, wbeg + wpw);
+    {
+      int run = 0;
+      for (int w = wbeg + lane; w < wbeg + wpw; w += 32) {
+        const int c = (w < wend) ? __popcll(bm[w]) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += y;
+        }
+        if (w < wend) pref[w] = (unsigned)(run + inc - c);
+        run += __shfl_sync(FULL, inc, 31);
+      }
+      __syncthreads();
+      if (lane == 0) s_red[warp] = run;
+      __syncthreads();
+    }
+    int wbase = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) wbase += (k < warp) ? s_red[k] : 0;
+    for (int w = wbeg + lane; w < wend; w += 32) pref[w] += (unsigned)wbase;
+    __syncthreads();
+    double* acc = Cval + Crp[i] + base;
+    int* ocol = Ccol + Crp[i] + base;
+    // ---- accumulators zeroed, columns emitted (see k_num_bitmap)
+    for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(acc + k, 0.0, pol_acc);
+    {
+      const int ngroups = (nwp + 31) >> 5;
+      const unsigned lt = lanemask_lt();
+      for (int g = warp; g < ngroups; g += NW) {
+        const int w = g * 32 + lane;
+        unsigned long long x = (w < nwp) ? bm[w] : 0ull;
+        int pos = (w < nwp) ? (int)pref[w] : 0;
+        const bool is_dense = __popcll(x) >= 16;
+        unsigned dense = __ballot_sync(FULL, is_dense);
+        while (dense) {
+          const int src = __ffs((int)dense) - 1;
+          dense &= dense - 1;
+          const unsigned long long xs = (unsigned long long)shfl64((long long)x, src);
+          const int ps = __shfl_sync(FULL, pos, src);
+          const unsigned lo32 = (unsigned)xs, hi32 = (unsigned)(xs >> 32);
+          const int cb = c_lo + (g * 32 + src) * 64;
+          if ((lo32 >> lane) & 1u) stg_hint(ocol + ps + __popc(lo32 & lt), cb + lane, pol_ocol);
+          if ((hi32 >> lane) & 1u)
+            stg_hint(ocol + ps + __popc(lo32) + __popc(hi32 & lt), cb + 32 + lane, pol_ocol);
+        }
+        if (is_dense) x = 0ull;
+        const int cb = c_lo + w * 64;
+        while (x) {
+          const int b = __ffsll((long long)x) - 1;
+          x &= x - 1;
+          stg_hint(ocol + pos++, cb + b, pol_ocol);
+        }
+      }
+    }
+    // ---- products of the part
+    auto accumulate = [&](int c, double prod) {
+      const int cc = c - c_lo;
+      const int w = cc >> 6;
+      const unsigned long long below = bm[w] & ((1ull << (cc & 63)) - 1ull);
+      red_add_hint(acc + (int)pref[w] + __popcll(below), prod, pol_acc);
+    };
+    __syncthreads();  // acc[] zeroed by every thread before the first RED lands
+    for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+      const int nb = (int)min((int64_t)BT, a1 - b0);
+      const long long total =
+          (batch0_ready && b0 == a0)
+              ? total0
+              : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
+      walk_run<BT, true>(ws, nb, total, Bcol, Bval, pol_b, accumulate);
+      __syncthreads();
+    }
+  }
+}
+
+// every row strictly ascending?  flag[0] is cleared by any violating pair
+__global__ void __launch_bounds__(256)
+k_check_sorted(const int64_t* __restrict__ rp, const int* __restrict__ col, int m,
+               int* __restrict__ flag) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  bool ok = true;
+  for (int64_t p = rp[warp] + 1 + lane; p < rp[warp + 1]; p += 32) ok &= col[p - 1] < col[p];
+  if (!ok) *flag = 0;
+}
+
 // keys for ordering a bitmap-bin list heaviest first: key[t] = flops[list[t]]
 __global__ void __launch_bounds__(256)
 k_gather_keys(const int* __restrict__ list, int count, const long long* __restrict__ flops,
@@ -1112,7 +1350,25 @@ int sort_rows_device(DevCSR* d) {
   dfree(d->val);
   d->col = col2;
   d->val = val2;
+  d->sorted_rows = true;
   B200_CUDA(cudaStreamSynchronize(c.stream));
+  return B200_OK;
+}
+
+int check_sorted_device(DevCSR* d) {
+  Ctx& c = ctx();
+  d->sorted_rows = true;
+  if (d->rows == 0 || d->nnz == 0) return B200_OK;
+  int* d_flag = nullptr;
+  int h = 1;
+  B200_CUDA(dalloc(&d_flag, 1));
+  B200_CUDA(cudaMemcpyAsync(d_flag, &h, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  const long long threads = (long long)d->rows * 32;
+  k_check_sorted<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d->rowptr, d->col, d->rows, d_flag);
+  B200_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  dfree(d_flag);
+  B200_CUDA(cudaStreamSynchronize(c.stream));
+  d->sorted_rows = h != 0;
   return B200_OK;
 }
 
@@ -1173,8 +1429,18 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   L2Modes l2m = {L2_LAST, L2_FIRST, L2_NORMAL, L2_FIRST, 0};
   if (const char* e = getenv("B200_L2POL"))
     sscanf(e, "%d,%d,%d,%d,%d", &l2m.acc, &l2m.ocol, &l2m.bgather, &l2m.bmstore, &l2m.demote);
+  // Part-wise numeric kernel (SpGEMM, sorted B rows): column parts of <= 8192 bitmap words so
+  // that two 512-thread CTAs fit one SM.
+  constexpr int BT_PART = 512;
+  const size_t walk_part_bytes = sizeof(WalkSmem<BT_PART>);
+  int nparts = (nw64 + 8191) / 8192;
+  int wpp = (((nw64 + nparts - 1) / nparts) + 63) & ~63;
+  const size_t part_smem = walk_part_bytes + (size_t)wpp * 12;
+  const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && sym_smem && nparts <= PARTS_MAX &&
+                         2 * (part_smem + 2048) <= c.smem_optin + 1024 && !getenv("B200_NO_PARTS");
+  if (!use_parts) { nparts = 1; wpp = nw64; }
   const long long sym_big_from = sym_smem ? 512 : 8192;
-  const int num_big_from = num_smem ? 256 : 2048;
+  const int num_big_from = (num_smem || use_parts) ? 256 : 2048;
 
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
@@ -1255,6 +1521,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
   B200_CUDA(dalloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
+  int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
+  if (use_parts) B200_CUDA(dalloc(&d_partcnt, (size_t)m * PARTS_MAX));
   const int nbig = sb.cnt[SB_BITMAP];
   int big_grid = std::min(nbig, c.sm_count);
   int store_rows = 0;
@@ -1273,12 +1541,14 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       if ((rc = set_smem(k_sym_bitmap<BT_BIG, true>, walk_bytes + bm_bytes))) return rc;
       k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, walk_bytes + bm_bytes, st>>>(
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
-          nw64, nullptr, d_bmstore, store_rows, d_bmslot, d_cnt, d_work + 0, l2m);
+          nw64, nullptr, d_bmstore, store_rows, d_bmslot, d_cnt, nparts, wpp, d_partcnt,
+          d_work + 0, l2m);
     } else {
       if ((rc = set_smem(k_sym_bitmap<BT_BIG, false>, walk_bytes))) return rc;
       k_sym_bitmap<BT_BIG, false><<<big_grid, BT_BIG, walk_bytes, st>>>(
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
-          nw64, d_gscr, d_bmstore, store_rows, d_bmslot, d_cnt, d_work + 0, l2m);
+          nw64, d_gscr, d_bmstore, store_rows, d_bmslot, d_cnt, nparts, wpp, d_partcnt,
+          d_work + 0, l2m);
     }
     tick(2 * SB_BITMAP + 1);
     ++launches;
@@ -1330,6 +1600,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (mode == MODE_SPGEMM) {
     C->rowptr = d_urp;
     C->nnz = unpruned;
+    C->sorted_rows = true;
     B200_CUDA(dalloc(&C->col, (size_t)unpruned));
     B200_CUDA(dalloc(&C->val, (size_t)unpruned));
   } else {
@@ -1405,7 +1676,14 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         d_gscr, d_bmstore, d_bmslot, d_urp, C->col, C->val, d_scr_col, d_scr_val, scr_stride,   \
         ro, d_work + 1, d_prof, l2m);                                                           \
   } while (0)
-    if (num_smem) {
+    if (use_parts) {
+      if ((rc = set_smem(k_num_bitmap_part<BT_PART>, part_smem))) return rc;
+      const long long items = (long long)nbig_num * nparts;
+      const int pgrid = (int)std::min<long long>(items, 2LL * c.sm_count);
+      k_num_bitmap_part<BT_PART><<<pgrid, BT_PART, part_smem, st>>>(
+          lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, nw64,
+          d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_work + 1, l2m);
+    } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(false, false); else LAUNCH_NUM_BM(false, true);
@@ -1474,7 +1752,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_bmstore); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmslot);
+  dfree(d_bmslot); dfree(d_partcnt);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {
