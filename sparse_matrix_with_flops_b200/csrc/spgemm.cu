@@ -597,7 +597,8 @@ struct WalkSmem {
   double a[BT];        // A value of the entry
   long long red[BT / 32 + 2];  // + total, + pad: the bitmap behind this struct is 16-byte aligned
 };
-static_assert(sizeof(WalkSmem<1024>) % 16 == 0 && sizeof(WalkSmem<512>) % 16 == 0,
+static_assert(sizeof(WalkSmem<1024>) % 16 == 0 && sizeof(WalkSmem<512>) % 16 == 0 &&
+                  sizeof(WalkSmem<256>) % 16 == 0,
               "bitmap must stay 16-byte aligned");
 
 // Walk the products of one A row with the whole CTA, FLAT: the products of a batch of up to BT
@@ -779,7 +780,7 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
              int nparts, int wpp, int* __restrict__ partcnt, int* __restrict__ work_counter,
              L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_red[BT / 32];
+  __shared__ int s_pc[BT / 32][PARTS_MAX];
   __shared__ int s_idx;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
@@ -798,29 +799,43 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
     cta_products_flat<BT, false>(a0, a1, Acol, (const double*)nullptr, Brp, Bcol,
                                  (const double*)nullptr, ws, pol_b,
                                  [&](int c, double) { bitmap_set(bm32, c); });
-    int cnt = 0;
-    int pc[PARTS_MAX] = {0, 0, 0, 0};  // columns per column part (see k_num_bitmap_part)
+    // count (per column part, see k_num_bitmap_part), store and clear in one sweep; wpp is a
+    // multiple of BT, so the part of a sweep step is the same for the whole CTA
+    int pc[PARTS_MAX] = {0, 0, 0, 0};
     unsigned long long* dst = (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 : nullptr;
-    for (int w = threadIdx.x; w < nw64; w += BT) {
-      const unsigned long long x = bm[w];
-      const int c = __popcll(x);
-      cnt += c;
-      if (nparts > 1) {
-        const int h = w / wpp;
+    for (int w0 = 0, h = 0, hnext = wpp; w0 < nw64; w0 += BT) {
+      const int w = w0 + threadIdx.x;
+      if (w0 >= hnext) { ++h; hnext += wpp; }
+      if (w < nw64) {
+        const unsigned long long x = bm[w];
+        const int c = __popcll(x);
 #pragma unroll
         for (int k = 0; k < PARTS_MAX; ++k) pc[k] += (k == h) ? c : 0;
+        if (dst) stg_hint(dst + w, x, pol_bm);
+        bm[w] = 0ull;
       }
-      if (dst) stg_hint(dst + w, x, pol_bm);
-      bm[w] = 0ull;
     }
-    cnt = block_sum_int<BT>(cnt, s_red);
-    if (nparts > 1) {
-      for (int k = 0; k < nparts; ++k) {
-        const int t = block_sum_int<BT>(pc[k], s_red);
-        if (threadIdx.x == 0) partcnt[(size_t)i * PARTS_MAX + k] = t;
+    {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int k = 0; k < PARTS_MAX; ++k) pc[k] = warp_sum_int(pc[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < PARTS_MAX; ++k) s_pc[warp][k] = pc[k];
       }
-    } else if (partcnt && threadIdx.x == 0) {
-      partcnt[(size_t)i * PARTS_MAX] = cnt;
+      __syncthreads();
+    }
+    int cnt = 0;
+    if (threadIdx.x == 0) {
+      int tot[PARTS_MAX] = {0, 0, 0, 0};
+      for (int wq = 0; wq < BT / 32; ++wq)
+#pragma unroll
+        for (int k = 0; k < PARTS_MAX; ++k) tot[k] += s_pc[wq][k];
+#pragma unroll
+      for (int k = 0; k < PARTS_MAX; ++k) cnt += tot[k];
+      if (partcnt)
+#pragma unroll
+        for (int k = 0; k < PARTS_MAX; ++k) partcnt[(size_t)i * PARTS_MAX + k] = tot[k];
     }
     if (threadIdx.x == 0) {
       rownnz[i] = cnt;
@@ -1091,8 +1106,8 @@ __device__ __forceinline__ long long walk_prepare_part(int64_t b0, int nb,
 // per SM and the serial phases of one item (ticket, bitmap load, prefix, column emission)
 // overlap the RED-bound product phase of the other.  Item (row, h) writes the slice of the
 // output row that starts partcnt[row][0..h) entries in.
-template <int BT>
-__global__ void __launch_bounds__(BT, 2)
+template <int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB)
 k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, int row_lo,
                   const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
                   const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
@@ -1121,15 +1136,45 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
     if (t >= items) break;
     const int i = list[t / nparts], h = t % nparts;
     const int* pc = partcnt + (size_t)i * PARTS_MAX;
-    const int cnt = pc[h];
-    if (cnt == 0) continue;
+    // pc[0] < 0: the row did not go through k_sym_bitmap (few products but many columns, or a
+    // single A entry), so its per-part counts are not known: they are counted here
+    const bool known = pc[0] >= 0;
+    if ((known && pc[h] == 0) || h * wpp >= nw64) continue;
+    const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+    const int slotno = bm_slot[i];
+    // builds in bm[] the bitmap of column part hh of this row
+    auto build_part = [&](int hh, bool reuse_batch0, long long total_b0) {
+      const int wl = hh * wpp, nw = min(wpp, nw64 - wl);
+      for (int w = threadIdx.x; w < nw; w += BT) bm[w] = 0ull;
+      __syncthreads();
+      for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+        const int nb = (int)min((int64_t)BT, a1 - b0);
+        const long long total =
+            (reuse_batch0 && b0 == a0)
+                ? total_b0
+                : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, wl * 64, (wl + nw) * 64,
+                                        hh == 0, hh == nparts - 1, ws);
+        walk_run<BT, false>(ws, nb, total, Bcol, (const double*)nullptr, pol_b,
+                            [&](int c, double) { bitmap_set(bm32, c - wl * 64); });
+        __syncthreads();
+      }
+    };
     int base = 0;
-    for (int k = 0; k < h; ++k) base += pc[k];
+    if (known) {
+      for (int k = 0; k < h; ++k) base += pc[k];
+    } else {
+      for (int hh = 0; hh < h; ++hh) {
+        build_part(hh, false, 0);
+        const int nw = min(wpp, nw64 - hh * wpp);
+        int c = 0;
+        for (int w = threadIdx.x; w < nw; w += BT) c += __popcll(bm[w]);
+        base += block_sum_int<BT>(c, s_red);
+        __syncthreads();
+      }
+    }
     const int w_lo = h * wpp, nwp = min(wpp, nw64 - w_lo);
     const int c_lo = w_lo * 64, c_hi = c_lo + nwp * 64;
     const bool first = h == 0, last = h == nparts - 1;
-    const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
-    const int slotno = bm_slot[i];
     // first batch of A entries: segments located, B lines requested from L2 ahead of use
     const int nb0 = (int)min((int64_t)BT, a1 - a0);
     const long long total0 =
@@ -1143,18 +1188,7 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(bm);
       for (int w = threadIdx.x; w < (nwp >> 1); w += BT) dst2[w] = ldg_hint(src + w, pol_bm);
     } else {
-      for (int w = threadIdx.x; w < nwp; w += BT) bm[w] = 0ull;
-      __syncthreads();
-      for (int64_t b0 = a0; b0 < a1; b0 += BT) {
-        const int nb = (int)min((int64_t)BT, a1 - b0);
-        const long long total =
-            (b0 == a0) ? total0
-                       : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, c_lo, c_hi, first,
-                                               last, ws);
-        walk_run<BT, false>(ws, nb, total, Bcol, (const double*)nullptr, pol_b,
-                            [&](int c, double) { bitmap_set(bm32, c - c_lo); });
-        __syncthreads();
-      }
+      build_part(h, true, total0);
       batch0_ready = (a1 - a0) <= BT;  // the walk area still holds batch 0 only then
     }
     __syncthreads();
@@ -1178,11 +1212,16 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       if (lane == 0) s_red[warp] = run;
       __syncthreads();
     }
-    int wbase = 0;
+    int wbase = 0, cnt = 0;
 #pragma unroll
-    for (int k = 0; k < NW; ++k) wbase += (k < warp) ? s_red[k] : 0;
+    for (int k = 0; k < NW; ++k) {
+      const int x = s_red[k];
+      wbase += (k < warp) ? x : 0;
+      cnt += x;
+    }
     for (int w = wbeg + lane; w < wend; w += 32) pref[w] += (unsigned)wbase;
     __syncthreads();
+    if (cnt == 0) continue;
     double* acc = Cval + Crp[i] + base;
     int* ocol = Ccol + Crp[i] + base;
     // ---- accumulators zeroed, columns emitted (see k_num_bitmap)
@@ -1431,13 +1470,16 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     sscanf(e, "%d,%d,%d,%d,%d", &l2m.acc, &l2m.ocol, &l2m.bgather, &l2m.bmstore, &l2m.demote);
   // Part-wise numeric kernel (SpGEMM, sorted B rows): column parts of <= 8192 bitmap words so
   // that two 512-thread CTAs fit one SM.
-  constexpr int BT_PART = 512;
-  const size_t walk_part_bytes = sizeof(WalkSmem<BT_PART>);
-  int nparts = (nw64 + 8191) / 8192;
-  int wpp = (((nw64 + nparts - 1) / nparts) + 63) & ~63;
+  const bool parts4 = getenv("B200_PARTS4") != nullptr;  // developer switch: 4 x 256 threads / SM
+  const int part_words_max = parts4 ? 4096 : 8192;
+  const int part_ctas = parts4 ? 4 : 2;
+  const size_t walk_part_bytes = parts4 ? sizeof(WalkSmem<256>) : sizeof(WalkSmem<512>);
+  int nparts = (nw64 + part_words_max - 1) / part_words_max;
+  int wpp = (((nw64 + nparts - 1) / nparts) + 1023) & ~1023;  // a multiple of the sweep step of k_sym_bitmap
   const size_t part_smem = walk_part_bytes + (size_t)wpp * 12;
   const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && sym_smem && nparts <= PARTS_MAX &&
-                         2 * (part_smem + 2048) <= c.smem_optin + 1024 && !getenv("B200_NO_PARTS");
+                         part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
+                         !getenv("B200_NO_PARTS");
   if (!use_parts) { nparts = 1; wpp = nw64; }
   const long long sym_big_from = sym_smem ? 512 : 8192;
   const int num_big_from = (num_smem || use_parts) ? 256 : 2048;
@@ -1522,7 +1564,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(dalloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
   int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
-  if (use_parts) B200_CUDA(dalloc(&d_partcnt, (size_t)m * PARTS_MAX));
+  if (use_parts) {
+    B200_CUDA(dalloc(&d_partcnt, (size_t)m * PARTS_MAX));
+    B200_CUDA(cudaMemsetAsync(d_partcnt, 0xff, (size_t)std::max(m, 1) * PARTS_MAX * sizeof(int), st));
+  }
   const int nbig = sb.cnt[SB_BITMAP];
   int big_grid = std::min(nbig, c.sm_count);
   int store_rows = 0;
@@ -1677,12 +1722,18 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         ro, d_work + 1, d_prof, l2m);                                                           \
   } while (0)
     if (use_parts) {
-      if ((rc = set_smem(k_num_bitmap_part<BT_PART>, part_smem))) return rc;
       const long long items = (long long)nbig_num * nparts;
-      const int pgrid = (int)std::min<long long>(items, 2LL * c.sm_count);
-      k_num_bitmap_part<BT_PART><<<pgrid, BT_PART, part_smem, st>>>(
-          lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, nw64,
-          d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_work + 1, l2m);
+      const int pgrid = (int)std::min<long long>(items, (long long)part_ctas * c.sm_count);
+
+#define LAUNCH_PART(BTP, MINB)                                                                  \
+  do {                                                                                          \
+    if ((rc = set_smem(k_num_bitmap_part<BTP, MINB>, part_smem))) return rc;                    \
+    k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
+        lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,     \
+        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_work + 1, l2m);          \
+  } while (0)
+      if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
+#undef LAUNCH_PART
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
