@@ -635,14 +635,22 @@ __device__ __forceinline__ long long walk_prepare(int64_t b0, int nb, const int*
 }
 
 // slice of the flat index space owned by this warp, and the entry holding its first index
+// (a team of CTAs can share one batch: member r of T takes the r-th T-th of the index space)
 template <int BT>
 __device__ __forceinline__ bool walk_slice(const WalkSmem<BT>& ws, int nb, long long total,
-                                           long long* xb, long long* xe, int* e0) {
+                                           long long* xb, long long* xe, int* e0, int r = 0,
+                                           int T = 1) {
   constexpr int NWARPS = BT / 32;
   const int warp = threadIdx.x >> 5;
-  const long long per_warp = (((total + NWARPS - 1) / NWARPS) + 31) & ~31LL;
-  *xb = (long long)warp * per_warp;
-  *xe = min(total, *xb + per_warp);
+  long long glo = 0, ghi = total;
+  if (T > 1) {
+    const long long per_member = (((total + T - 1) / T) + 31) & ~31LL;
+    glo = min(total, (long long)r * per_member);
+    ghi = min(total, glo + per_member);
+  }
+  const long long per_warp = ((((ghi - glo) + NWARPS - 1) / NWARPS) + 31) & ~31LL;
+  *xb = glo + (long long)warp * per_warp;
+  *xe = min(ghi, *xb + per_warp);
   if (*xb >= *xe) return false;
   int lo = 0, hi = nb - 1;  // xb < total guarantees an answer
   while (lo < hi) {
@@ -656,10 +664,11 @@ __device__ __forceinline__ bool walk_slice(const WalkSmem<BT>& ws, int nb, long 
 template <int BT, bool WITH_VAL>
 __device__ __forceinline__ void walk_prefetch(const WalkSmem<BT>& ws, int nb, long long total,
                                               const int* __restrict__ Bcol,
-                                              const double* __restrict__ Bval) {
+                                              const double* __restrict__ Bval, int r = 0,
+                                              int T = 1) {
   long long xb, xe;
   int e;
-  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e)) return;
+  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e, r, T)) return;
   const int lane = threadIdx.x & 31;
   // lane l looks after the 32-index step starting at xb + 32*l (then +1024, ...): one line of
   // columns and two of values per step, addressed by the step's first element
@@ -678,10 +687,10 @@ template <int BT, bool WITH_VAL, typename F>
 __device__ __forceinline__ void walk_run(const WalkSmem<BT>& ws, int nb, long long total,
                                          const int* __restrict__ Bcol,
                                          const double* __restrict__ Bval, unsigned long long bpol,
-                                         F f) {
+                                         F f, int r = 0, int T = 1) {
   long long xb, xe;
   int e;
-  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e)) return;
+  if (!walk_slice<BT>(ws, nb, total, &xb, &xe, &e, r, T)) return;
   const int lane = threadIdx.x & 31;
   long long x = xb + lane;
   // eight products in flight while they all lie in one B row (long rows: the common case)
@@ -1115,10 +1124,11 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
                   const unsigned long long* __restrict__ bm_store,
                   const int* __restrict__ bm_slot, const int* __restrict__ partcnt,
                   const int64_t* __restrict__ Crp, int* __restrict__ Ccol,
-                  double* __restrict__ Cval, int* __restrict__ work_counter, L2Modes l2) {
+                  double* __restrict__ Cval, const int* __restrict__ itemoff,
+                  int* __restrict__ team_ready, int* __restrict__ work_counter, L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
-  __shared__ int s_idx;
+  __shared__ int s_idx, s_slot;
   constexpr int NW = BT / 32;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>));
@@ -1127,14 +1137,37 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long pol_acc = l2_policy(l2.acc), pol_ocol = l2_policy(l2.ocol),
                            pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
-  const int items = count * nparts;
+  // Work items: (row, column part) slot q = listpos * nparts + h owns the tickets
+  // [itemoff[q], itemoff[q+1]) — a TEAM of T CTAs for a heavy slot (T ~ products / 96K), one
+  // CTA otherwise (tuned on R-MAT scale 20: 96K).  Teams bound how many distinct accumulator slices are in flight (296 CTAs
+  // of hub rows would keep ~1 GB of accumulators live and every RED would miss L2) and make
+  // item durations uniform.  Team members split the zeroing, the column emission and the
+  // products; a member starts its REDs only after all members have zeroed their share
+  // (team_ready counter; members hold consecutive tickets, and a CTA only ever waits for
+  // holders of earlier-or-adjacent tickets that are already resident or will be fetched next,
+  // never the other way round, so the wait cannot deadlock).
+  const int nslots = count * nparts;
+  const int tickets = itemoff[nslots];
   while (true) {
     __syncthreads();
-    if (threadIdx.x == 0) s_idx = atomicAdd(work_counter, 1);
+    if (threadIdx.x == 0) {
+      const int t = atomicAdd(work_counter, 1);
+      s_idx = t;
+      if (t < tickets) {  // slot q with itemoff[q] <= t < itemoff[q+1]
+        int lo = 0, hi = nslots - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (itemoff[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        s_slot = lo;
+      }
+    }
     __syncthreads();
     const int t = s_idx;
-    if (t >= items) break;
-    const int i = list[t / nparts], h = t % nparts;
+    if (t >= tickets) break;
+    const int q = s_slot;
+    const int team_T = itemoff[q + 1] - itemoff[q], team_r = t - itemoff[q];
+    const int i = list[q / nparts], h = q % nparts;
     const int* pc = partcnt + (size_t)i * PARTS_MAX;
     // pc[0] < 0: the row did not go through k_sym_bitmap (few products but many columns, or a
     // single A entry), so its per-part counts are not known: they are counted here
@@ -1179,7 +1212,7 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
     const int nb0 = (int)min((int64_t)BT, a1 - a0);
     const long long total0 =
         walk_prepare_part<BT>(a0, nb0, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
-    walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval);
+    walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval, team_r, team_T);
     bool batch0_ready = true;
     // ---- the part's bitmap
     if (slotno >= 0) {
@@ -1224,12 +1257,16 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
     if (cnt == 0) continue;
     double* acc = Cval + Crp[i] + base;
     int* ocol = Ccol + Crp[i] + base;
-    // ---- accumulators zeroed, columns emitted (see k_num_bitmap)
-    for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(acc + k, 0.0, pol_acc);
+    // ---- this member's share of the accumulators zeroed and of the columns emitted
+    {
+      const int per = (cnt + team_T - 1) / team_T;
+      const int k1 = min(cnt, (team_r + 1) * per);
+      for (int k = team_r * per + threadIdx.x; k < k1; k += BT) stg_hint(acc + k, 0.0, pol_acc);
+    }
     {
       const int ngroups = (nwp + 31) >> 5;
       const unsigned lt = lanemask_lt();
-      for (int g = warp; g < ngroups; g += NW) {
+      for (int g = warp + NW * team_r; g < ngroups; g += NW * team_T) {
         const int w = g * 32 + lane;
         unsigned long long x = (w < nwp) ? bm[w] : 0ull;
         int pos = (w < nwp) ? (int)pref[w] : 0;
@@ -1262,17 +1299,49 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       const unsigned long long below = bm[w] & ((1ull << (cc & 63)) - 1ull);
       red_add_hint(acc + (int)pref[w] + __popcll(below), prod, pol_acc);
     };
-    __syncthreads();  // acc[] zeroed by every thread before the first RED lands
+    __syncthreads();  // acc[] zeroed by every thread of this CTA before its first RED lands
+    if (team_T > 1) {   // ... and by every other member of the team
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(team_ready + q, 1);
+        while (*(volatile int*)(team_ready + q) < team_T) __nanosleep(200);
+        __threadfence();
+      }
+      __syncthreads();
+    }
     for (int64_t b0 = a0; b0 < a1; b0 += BT) {
       const int nb = (int)min((int64_t)BT, a1 - b0);
       const long long total =
           (batch0_ready && b0 == a0)
               ? total0
               : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
-      walk_run<BT, true>(ws, nb, total, Bcol, Bval, pol_b, accumulate);
+      walk_run<BT, true>(ws, nb, total, Bcol, Bval, pol_b, accumulate, team_r, team_T);
       __syncthreads();
     }
   }
+}
+
+// team size of every (row, part) slot of the part-wise numeric kernel: 0 for an empty part,
+// else ceil(products of the row / nparts / team_products), at most team_max
+__global__ void __launch_bounds__(256)
+k_team_sizes(const int* __restrict__ list, int count, int nparts,
+             const long long* __restrict__ flops, const int* __restrict__ partcnt,
+             long long team_products, int team_max, int* __restrict__ tsize) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count * nparts) return;
+  const int i = list[q / nparts], h = q % nparts;
+  const int* pc = partcnt + (size_t)i * PARTS_MAX;
+  int T = 1;
+  if (pc[0] >= 0) {
+    if (pc[h] == 0) T = 0;
+    else {
+      int nonempty = 0;
+      for (int k = 0; k < nparts; ++k) nonempty += pc[k] > 0;
+      const long long share = flops[i] / max(1, nonempty);
+      T = (int)min((long long)team_max, max(1LL, (share + team_products - 1) / team_products));
+    }
+  }
+  tsize[q] = T;
 }
 
 // every row strictly ascending?  flag[0] is cleared by any violating pair
@@ -1563,6 +1632,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
   B200_CUDA(dalloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
+  int* d_itemoff = nullptr;  // ticket offsets of the (row, part) slots of k_num_bitmap_part
   int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
   if (use_parts) {
     B200_CUDA(dalloc(&d_partcnt, (size_t)m * PARTS_MAX));
@@ -1722,18 +1792,41 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         ro, d_work + 1, d_prof, l2m);                                                           \
   } while (0)
     if (use_parts) {
-      const long long items = (long long)nbig_num * nparts;
-      const int pgrid = (int)std::min<long long>(items, (long long)part_ctas * c.sm_count);
+      // team sizes -> ticket offsets of the (row, part) slots
+      const int nslots = nbig_num * nparts;
+      int* d_tsize = nullptr;
+      int* d_ready = nullptr;
+      B200_CUDA(dalloc(&d_tsize, (size_t)nslots + 1));
+      B200_CUDA(dalloc(&d_itemoff, (size_t)nslots + 1));
+      B200_CUDA(dalloc(&d_ready, (size_t)nslots));
+      B200_CUDA(cudaMemsetAsync(d_tsize + nslots, 0, sizeof(int), st));
+      B200_CUDA(cudaMemsetAsync(d_ready, 0, (size_t)nslots * sizeof(int), st));
+      const long long team_products = getenv("B200_TEAM_P") ? atoll(getenv("B200_TEAM_P")) : 98304;
+      const int team_max = getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64;
+      k_team_sizes<<<(nslots + 255) / 256, 256, 0, st>>>(lst, nbig_num, nparts, d_flops, d_partcnt,
+                                                         team_products, team_max, d_tsize);
+      {
+        void* tmp = nullptr;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_tsize, d_itemoff, nslots + 1, st);
+        B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, st));
+        cub::DeviceScan::ExclusiveSum(tmp, tb, d_tsize, d_itemoff, nslots + 1, st);
+        cudaFreeAsync(tmp, st);
+      }
+      launches += 2;
+      const int pgrid = part_ctas * c.sm_count;  // all resident: team members wait for each other
 
 #define LAUNCH_PART(BTP, MINB)                                                                  \
   do {                                                                                          \
     if ((rc = set_smem(k_num_bitmap_part<BTP, MINB>, part_smem))) return rc;                    \
     k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
         lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,     \
-        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_work + 1, l2m);          \
+        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_itemoff, d_ready,        \
+        d_work + 1, l2m);                                                                       \
   } while (0)
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
+      dfree(d_tsize); dfree(d_ready);
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
@@ -1803,7 +1896,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_bmstore); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmslot); dfree(d_partcnt);
+  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {
