@@ -95,6 +95,11 @@ __device__ __forceinline__ long long shfl64(long long v, int src) {
   int hi = __shfl_sync(FULL, (int)(v >> 32), src);
   return ((long long)hi << 32) | (unsigned)lo;
 }
+__device__ __forceinline__ long long shfl64_xor(long long v, int m) {
+  int lo = __shfl_xor_sync(FULL, (int)(v & 0xffffffffLL), m);
+  int hi = __shfl_xor_sync(FULL, (int)(v >> 32), m);
+  return ((long long)hi << 32) | (unsigned)lo;
+}
 __device__ __forceinline__ double shfld(double v, int src) {
   return __longlong_as_double(shfl64(__double_as_longlong(v), src));
 }
@@ -181,22 +186,32 @@ __device__ __forceinline__ double compute_threshold(double avg, double mx) {
 
 // ------------------------------------------------------------------------------------------
 // flops analysis: P_i = sum_{j in A_i} nnz(B_j)  (flops_csr_kernel.cc:14-31)
-// one thread per row; also emits the symbolic bin and, for rows that need no hashing, nnz(C_i).
+// Eight lanes per row (a hub row of 30 000 entries walked by one thread would be the whole
+// kernel's critical path); also emits the symbolic bin and, for rows that need no hashing,
+// nnz(C_i).
 __global__ void __launch_bounds__(256)
 k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
             const int64_t* __restrict__ Brp, int row_lo, int m, long long big_from,
             long long* __restrict__ flops, unsigned char* __restrict__ sbin,
             int* __restrict__ rownnz) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gt >> 3), sub = (int)(gt & 7);
+  const bool live = i < m;
   long long f = 0;
-  for (int64_t p = a0; p < a1; ++p) {
-    int j = __ldg(Acol + p);
-    f += __ldg(Brp + j + 1) - __ldg(Brp + j);
+  int64_t a0 = 0, a1 = 0;
+  if (live) {
+    a0 = Arp[row_lo + i];
+    a1 = Arp[row_lo + i + 1];
+    for (int64_t p = a0 + sub; p < a1; p += 8) {
+      const int j = __ldg(Acol + p);
+      f += __ldg(Brp + j + 1) - __ldg(Brp + j);
+    }
   }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) f += shfl64_xor(f, o);
+  if (!live || sub != 0) return;
   flops[i] = f;
-  int b = sym_bin_of(f, (int)(a1 - a0), big_from);
+  const int b = sym_bin_of(f, (int)(a1 - a0), big_from);
   sbin[i] = (unsigned char)b;
   if (b == SB_NONE) rownnz[i] = (int)f;  // 0, or the length of the single B row
 }
@@ -745,6 +760,71 @@ __device__ __forceinline__ void walk_run(const WalkSmem<BT>& ws, int nb, long lo
   }
 }
 
+// walk_run with DYNAMIC distribution: the warps of the CTA draw chunks of CH consecutive flat
+// indices of [glo, ghi) from a shared counter (*next, set to glo by the caller before a
+// barrier), so a warp that was served from L2 takes more chunks than one that waited for DRAM
+// and the CTA reaches the closing barrier together.  One binary search per chunk.
+template <int BT, int CH, bool WITH_VAL, typename F>
+__device__ __forceinline__ void walk_run_dynamic(const WalkSmem<BT>& ws, int nb, long long glo,
+                                                 long long ghi, long long* next,
+                                                 const int* __restrict__ Bcol,
+                                                 const double* __restrict__ Bval,
+                                                 unsigned long long bpol, F f) {
+  static_assert(CH % 128 == 0, "a chunk is a whole number of 4-deep warp steps");
+  const int lane = threadIdx.x & 31;
+  while (true) {
+    long long xb = 0;
+    if (lane == 0) xb = (long long)atomicAdd((unsigned long long*)next, (unsigned long long)CH);
+    xb = shfl64(xb, 0);
+    if (xb >= ghi) break;
+    const long long xe = min(ghi, xb + CH);
+    int e;
+    {
+      int lo = 0, hi = nb - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (xb < ws.end[mid]) hi = mid; else lo = mid + 1;
+      }
+      e = lo;
+    }
+    long long x = xb + lane;
+    for (; x + 96 < xe; x += 128) {
+      long long q[4];
+      double av[4];
+      while (x >= ws.end[e]) ++e;
+      if (x + 96 < ws.end[e]) {
+        const long long base = ws.base[e] + x;
+        const double a = ws.a[e];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { q[u] = base + 32 * u; av[u] = a; }
+      } else {
+        int eu = e;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          while (x + 32 * u >= ws.end[eu]) ++eu;
+          q[u] = ws.base[eu] + x + 32 * u;
+          av[u] = ws.a[eu];
+        }
+      }
+      int col[4];
+      double bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        col[u] = ldg_hint(Bcol + q[u], bpol);
+        if (WITH_VAL) bv[u] = ldg_hint(Bval + q[u], bpol);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f(col[u], WITH_VAL ? __dmul_rn(av[u], bv[u]) : 0.0);
+    }
+    for (; x < xe; x += 32) {
+      while (x >= ws.end[e]) ++e;
+      const long long q = ws.base[e] + x;
+      const int col = ldg_hint(Bcol + q, bpol);
+      f(col, WITH_VAL ? __dmul_rn(ws.a[e], ldg_hint(Bval + q, bpol)) : 0.0);
+    }
+  }
+}
+
 // prepare + run over every batch of the row (no early prefetch)
 template <int BT, bool WITH_VAL, typename F>
 __device__ __forceinline__ void cta_products_flat(int64_t a0, int64_t a1,
@@ -1078,25 +1158,37 @@ __device__ __forceinline__ long long lower_bound_col(const int* __restrict__ col
   return lo;
 }
 
-// walk_prepare restricted to the columns [c_lo, c_hi) of every B row (rows sorted): the
-// segment of a B row inside the part is found with binary searches, so the products outside
-// the part are never read
+// offsets of the column-part boundaries inside every (sorted) B row: one binary search per row
+// and boundary, once per call, instead of one per A entry and work item
+__global__ void __launch_bounds__(256)
+k_bsplit(const int64_t* __restrict__ Brp, const int* __restrict__ Bcol, int krows, int nparts,
+         int wpp, int* __restrict__ bsplit) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)krows * (nparts - 1)) return;
+  const int p = (int)(t / krows) + 1, j = (int)(t % krows);
+  const long long s = Brp[j], e = Brp[j + 1];
+  bsplit[t] = (int)(lower_bound_col(Bcol, s, e, p * wpp * 64) - s);
+}
+
+// walk_prepare restricted to one column part of every B row (rows sorted): the segment of a B
+// row inside the part comes from the k_bsplit table, so the products outside the part are
+// never read
 template <int BT>
 __device__ __forceinline__ long long walk_prepare_part(int64_t b0, int nb,
                                                        const int* __restrict__ Acol,
                                                        const double* __restrict__ Aval,
                                                        const int64_t* __restrict__ Brp,
-                                                       const int* __restrict__ Bcol, int c_lo,
-                                                       int c_hi, bool first, bool last,
-                                                       WalkSmem<BT>& ws) {
+                                                       const int* __restrict__ bsplit, int krows,
+                                                       int h, int nparts, WalkSmem<BT>& ws) {
   long long len = 0, bs = 0;
   double a = 0.0;
   if ((int)threadIdx.x < nb) {
     const int j = __ldg(Acol + b0 + threadIdx.x);
     a = __ldg(Aval + b0 + threadIdx.x);
-    long long s = __ldg(Brp + j), e = __ldg(Brp + j + 1);
-    if (!first) s = lower_bound_col(Bcol, s, e, c_lo);
-    if (!last) e = lower_bound_col(Bcol, s, e, c_hi);
+    // bsplit[(p-1)*krows + j]: offset inside B row j of its first column of part p (k_bsplit)
+    const long long r0 = __ldg(Brp + j);
+    const long long s = (h == 0) ? r0 : r0 + __ldg(bsplit + (size_t)(h - 1) * krows + j);
+    const long long e = (h == nparts - 1) ? __ldg(Brp + j + 1) : r0 + __ldg(bsplit + (size_t)h * krows + j);
     bs = s;
     len = e - s;
   }
@@ -1125,10 +1217,12 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
                   const int* __restrict__ bm_slot, const int* __restrict__ partcnt,
                   const int64_t* __restrict__ Crp, int* __restrict__ Ccol,
                   double* __restrict__ Cval, const int* __restrict__ itemoff,
-                  int* __restrict__ team_ready, int* __restrict__ work_counter, L2Modes l2) {
+                  int* __restrict__ team_ready, const int* __restrict__ bsplit, int krows,
+                  int* __restrict__ work_counter, L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
   __shared__ int s_idx, s_slot;
+  __shared__ long long s_next;
   constexpr int NW = BT / 32;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>));
@@ -1185,8 +1279,7 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
         const long long total =
             (reuse_batch0 && b0 == a0)
                 ? total_b0
-                : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, wl * 64, (wl + nw) * 64,
-                                        hh == 0, hh == nparts - 1, ws);
+                : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, bsplit, krows, hh, nparts, ws);
         walk_run<BT, false>(ws, nb, total, Bcol, (const double*)nullptr, pol_b,
                             [&](int c, double) { bitmap_set(bm32, c - wl * 64); });
         __syncthreads();
@@ -1206,12 +1299,11 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       }
     }
     const int w_lo = h * wpp, nwp = min(wpp, nw64 - w_lo);
-    const int c_lo = w_lo * 64, c_hi = c_lo + nwp * 64;
-    const bool first = h == 0, last = h == nparts - 1;
+    const int c_lo = w_lo * 64;
     // first batch of A entries: segments located, B lines requested from L2 ahead of use
     const int nb0 = (int)min((int64_t)BT, a1 - a0);
     const long long total0 =
-        walk_prepare_part<BT>(a0, nb0, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
+        walk_prepare_part<BT>(a0, nb0, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
     walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval, team_r, team_T);
     bool batch0_ready = true;
     // ---- the part's bitmap
@@ -1314,8 +1406,14 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       const long long total =
           (batch0_ready && b0 == a0)
               ? total0
-              : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, Bcol, c_lo, c_hi, first, last, ws);
-      walk_run<BT, true>(ws, nb, total, Bcol, Bval, pol_b, accumulate, team_r, team_T);
+              : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
+      // this member's share of the batch, drawn by its warps in chunks
+      const long long per_member = (((total + team_T - 1) / team_T) + 31) & ~31LL;
+      const long long glo = min(total, (long long)team_r * per_member);
+      const long long ghi = min(total, glo + per_member);
+      if (threadIdx.x == 0) s_next = glo;
+      __syncthreads();
+      walk_run_dynamic<BT, 512, true>(ws, nb, glo, ghi, &s_next, Bcol, Bval, pol_b, accumulate);
       __syncthreads();
     }
   }
@@ -1493,8 +1591,8 @@ int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi
   B200_CUDA(dalloc(&d_cnt, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_flops + m, 0, sizeof(long long), c.stream));
   if (m > 0)
-    k_row_flops<<<(m + 255) / 256, 256, 0, c.stream>>>(A.rowptr, A.col, B.rowptr, row_lo, m,
-                                                       8192LL, d_flops, d_bin, d_cnt);
+    k_row_flops<<<(unsigned)(((long long)m * 8 + 255) / 256), 256, 0, c.stream>>>(
+        A.rowptr, A.col, B.rowptr, row_lo, m, 8192LL, d_flops, d_bin, d_cnt);
   void* tmp = nullptr;
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flops, (long long*)d_prefix, m + 1, c.stream);
@@ -1563,8 +1661,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(dalloc(&d_cnt, (size_t)m + 1));
   B200_CUDA(dalloc(&d_P, 2));
   if (m > 0) {
-    k_row_flops<<<(m + 255) / 256, 256, 0, st>>>(A.rowptr, A.col, B.rowptr, row_lo, m,
-                                                 sym_big_from, d_flops, d_bin, d_cnt);
+    k_row_flops<<<(unsigned)(((long long)m * 8 + 255) / 256), 256, 0, st>>>(
+        A.rowptr, A.col, B.rowptr, row_lo, m, sym_big_from, d_flops, d_bin, d_cnt);
     ++launches;
   }
   {
@@ -1801,6 +1899,14 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(dalloc(&d_ready, (size_t)nslots));
       B200_CUDA(cudaMemsetAsync(d_tsize + nslots, 0, sizeof(int), st));
       B200_CUDA(cudaMemsetAsync(d_ready, 0, (size_t)nslots * sizeof(int), st));
+      // column-part boundaries inside every B row
+      int* d_bsplit = nullptr;
+      B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
+      if (nparts > 1) {
+        const long long nt = (long long)B.rows * (nparts - 1);
+        k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
+        ++launches;
+      }
       const long long team_products = getenv("B200_TEAM_P") ? atoll(getenv("B200_TEAM_P")) : 98304;
       const int team_max = getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64;
       k_team_sizes<<<(nslots + 255) / 256, 256, 0, st>>>(lst, nbig_num, nparts, d_flops, d_partcnt,
@@ -1822,11 +1928,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
         lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,     \
         nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_itemoff, d_ready,        \
-        d_work + 1, l2m);                                                                       \
+        d_bsplit, B.rows, d_work + 1, l2m);                                                     \
   } while (0)
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
-      dfree(d_tsize); dfree(d_ready);
+      dfree(d_tsize); dfree(d_ready); dfree(d_bsplit);
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
