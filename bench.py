@@ -292,7 +292,8 @@ def run_b200(args):
     ends = smf.arrayEqualPartition64(prefix, world)
     lo, hi = int(ends[rank]), int(ends[rank + 1])
 
-    acc = {"sym": np.zeros(16), "num": np.zeros(16), "launches": 0, "last": None}
+    acc = {"sym": np.zeros(16), "num": np.zeros(16), "launches": 0, "last": None,
+           "phases": np.zeros(5)}
 
     def step(record):
         dC, st = smf.gpuSpMMWrapper(dA, dA, lo, hi, want_stats=True)
@@ -301,6 +302,8 @@ def run_b200(args):
             acc["sym"] += np.array(st["ms_sym_bin"])
             acc["num"] += np.array(st["ms_num_bin"])
             acc["launches"] += st["launches"]
+            acc["phases"] += np.array([st["ms_total"], st["ms_flops"], st["ms_symbolic"],
+                                       st["ms_numeric"], st["ms_other"]])
             acc["last"] = st
 
     for _ in range(args.warmup):
@@ -339,6 +342,8 @@ def run_b200(args):
             cands.append((acc["sym"][b] / args.steps, "sym", b, nm))
     for b, nm in NUM_KERNELS.items():
         if acc["num"][b] > 0:
+            if b == 5 and st.get("part_kernel"):
+                nm = "k_num_bitmap_part"
             cands.append((acc["num"][b] / args.steps, "num", b, nm))
     cands.sort(reverse=True)
     kms, kind, b, kname = cands[0]
@@ -362,7 +367,9 @@ def run_b200(args):
                 "kernel_algorithmic_bytes": kb,
                 "step_algorithmic_bytes": step_bytes,
                 "step_frac": (step_bytes / (ms_step * 1e-3) / 1e9 / peak) if step_bytes else None,
-                "kernels_ms": {nm: round(ms_, 4) for ms_, _, _, nm in cands}}
+                "kernels_ms": {nm: round(ms_, 4) for ms_, _, _, nm in cands},
+                "phases_ms": dict(zip(["call", "flops_binning", "symbolic", "numeric", "scans_alloc"],
+                                      [round(float(x) / args.steps, 3) for x in acc["phases"]]))}
 
     # ---- e2e through the host-buffer C-ABI ------------------------------------------------
     e2e = None

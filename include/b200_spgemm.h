@@ -61,6 +61,8 @@ typedef struct b200_stats {
   double ms_num_bin[16];
   long long sym_bin_rows[16], sym_bin_products[16], sym_bin_nnzA[16];
   long long num_bin_products[16], num_bin_nnzA[16], num_bin_nnzC[16];
+  int part_kernel;     /* 1: the bitmap bin's numeric pass ran as k_num_bitmap_part */
+  int part_count;      /* column parts it used */
 } b200_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -37,6 +37,8 @@ class Stats(C.Structure):
         ("num_bin_products", C.c_longlong * 16),
         ("num_bin_nnzA", C.c_longlong * 16),
         ("num_bin_nnzC", C.c_longlong * 16),
+        ("part_kernel", C.c_int),
+        ("part_count", C.c_int),
     ]
 
     def as_dict(self):

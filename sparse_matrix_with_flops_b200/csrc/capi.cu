@@ -3,6 +3,7 @@
 #include <limits.h>
 #include <stdint.h>
 #include <sys/mman.h>
+#include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -64,7 +65,7 @@ __global__ void k_row_argmax(const int64_t* __restrict__ rp, const int* __restri
 // thread plus first-touch page faults).  Instead: DMA through two pinned buffers on a second
 // stream while all host cores copy the previous chunk between the pinned buffer and the user's
 // block (which also first-touches a fresh malloc block in parallel).
-constexpr size_t PIN_BYTES = 64u << 20;
+constexpr size_t PIN_BYTES = 128u << 20;
 
 int ensure_staging() {
   Ctx& c = ctx();
@@ -88,13 +89,15 @@ void advise_huge(void* p, size_t bytes) {
   if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 }
 
+// one contiguous piece per host thread (large pieces let memcpy use non-temporal stores, which
+// spare the destination the read-for-ownership of a regular store)
 void parallel_copy(void* dst, const void* src, size_t bytes) {
-  const size_t piece = 1u << 20;
-  const long long pieces = (long long)((bytes + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
-  for (long long t = 0; t < pieces; ++t) {
-    const size_t off = (size_t)t * piece;
-    memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
+#pragma omp parallel
+  {
+    const size_t nt = (size_t)omp_get_num_threads(), t = (size_t)omp_get_thread_num();
+    const size_t piece = (((bytes + nt - 1) / nt) + 4095) & ~(size_t)4095;
+    const size_t off = t * piece;
+    if (off < bytes) memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
   }
 }
 
@@ -271,6 +274,7 @@ int b200_finalize(void) {
   cudaStreamSynchronize(c.stream);
   for (auto& ev : c.ev) { cudaEventDestroy(ev); ev = nullptr; }
   for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
+  if (c.bm_store) { cudaFree(c.bm_store); c.bm_store = nullptr; c.bm_store_words = 0; }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   if (c.pin[0]) {

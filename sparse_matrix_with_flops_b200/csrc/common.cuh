@@ -47,6 +47,10 @@ struct Ctx {
   void* pin[2] = {nullptr, nullptr};
   cudaEvent_t pin_ev[2] = {};
   cudaEvent_t xfer_ev = nullptr;
+  // bitmap store of the symbolic pass, kept between calls (re-allocating tens of GB from the
+  // stream-ordered pool every call costs ~10 ms of remapping)
+  unsigned long long* bm_store = nullptr;
+  size_t bm_store_words = 0;
 };
 Ctx& ctx();
 

@@ -1419,6 +1419,84 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
   }
 }
 
+// symbolic for large rows, PART-WISE (same geometry as k_num_bitmap_part: 512 threads, the
+// part's bitmap in shared memory, two CTAs per SM).  Item (row, part) counts the distinct
+// columns of the row inside the part (partcnt), and keeps the part's bitmap in the store for
+// the numeric pass when the row has a slot there.  rownnz = sum of the parts (k_sum_parts).
+template <int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB)
+k_sym_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, int row_lo,
+                  const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
+                  const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
+                  const int* __restrict__ Bcol, int nw64,
+                  unsigned long long* __restrict__ bm_store, int store_rows,
+                  int* __restrict__ bm_slot, int* __restrict__ partcnt,
+                  const int* __restrict__ bsplit, int krows, int* __restrict__ work_counter,
+                  L2Modes l2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_red[BT / 32];
+  __shared__ int s_idx;
+  __shared__ long long s_next;
+  WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
+  unsigned long long* bm = (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>));
+  unsigned* bm32 = (unsigned*)bm;
+  const unsigned long long pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
+  const int items = count * nparts;
+  for (int w = threadIdx.x; w < wpp; w += BT) bm[w] = 0ull;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int t = s_idx;
+    if (t >= items) break;
+    const int idx = t / nparts, h = t % nparts;
+    const int i = list[idx];
+    const int w_lo = h * wpp, nwp = min(wpp, nw64 - w_lo);
+    if (nwp <= 0) {
+      if (threadIdx.x == 0) partcnt[(size_t)i * PARTS_MAX + h] = 0;
+      continue;
+    }
+    const int c_lo = w_lo * 64;
+    const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+    for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+      const int nb = (int)min((int64_t)BT, a1 - b0);
+      const long long total =
+          walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
+      if (threadIdx.x == 0) s_next = 0;
+      __syncthreads();
+      walk_run_dynamic<BT, 512, false>(ws, nb, 0, total, &s_next, Bcol, (const double*)nullptr,
+                                       pol_b, [&](int c, double) { bitmap_set(bm32, c - c_lo); });
+      __syncthreads();
+    }
+    int cnt = 0;
+    unsigned long long* dst =
+        (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 + w_lo : nullptr;
+    for (int w = threadIdx.x; w < nwp; w += BT) {
+      const unsigned long long x = bm[w];
+      cnt += __popcll(x);
+      if (dst) stg_hint(dst + w, x, pol_bm);
+      bm[w] = 0ull;
+    }
+    cnt = block_sum_int<BT>(cnt, s_red);
+    if (threadIdx.x == 0) {
+      partcnt[(size_t)i * PARTS_MAX + h] = cnt;
+      if (h == 0) bm_slot[i] = dst ? idx : -1;
+    }
+  }
+}
+
+// rownnz[i] = sum over parts of partcnt[i][.] for the rows of a list
+__global__ void __launch_bounds__(256)
+k_sum_parts(const int* __restrict__ list, int count, int nparts, const int* __restrict__ partcnt,
+            int* __restrict__ rownnz) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int i = list[t];
+  int s = 0;
+  for (int k = 0; k < nparts; ++k) s += partcnt[(size_t)i * PARTS_MAX + k];
+  rownnz[i] = s;
+}
+
 // team size of every (row, part) slot of the part-wise numeric kernel: 0 for an empty part,
 // else ceil(products of the row / nparts / team_products), at most team_max
 __global__ void __launch_bounds__(256)
@@ -1644,11 +1722,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int nparts = (nw64 + part_words_max - 1) / part_words_max;
   int wpp = (((nw64 + nparts - 1) / nparts) + 1023) & ~1023;  // a multiple of the sweep step of k_sym_bitmap
   const size_t part_smem = walk_part_bytes + (size_t)wpp * 12;
-  const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && sym_smem && nparts <= PARTS_MAX &&
+  const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && nparts <= PARTS_MAX &&
                          part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
                          !getenv("B200_NO_PARTS");
   if (!use_parts) { nparts = 1; wpp = nw64; }
-  const long long sym_big_from = sym_smem ? 512 : 8192;
+  const long long sym_big_from = (sym_smem || use_parts) ? 512 : 8192;
   const int num_big_from = (num_smem || use_parts) ? 256 : 2048;
 
   // ---- 1. flops analysis + symbolic binning
@@ -1730,6 +1808,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
   B200_CUDA(dalloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
+  int* d_bsplit = nullptr;   // column-part boundaries inside every B row (k_bsplit)
   int* d_itemoff = nullptr;  // ticket offsets of the (row, part) slots of k_num_bitmap_part
   int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
   if (use_parts) {
@@ -1740,17 +1819,55 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int big_grid = std::min(nbig, c.sm_count);
   int store_rows = 0;
   if (nbig) {
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    // keep the bitmaps of the heaviest rows while they use a modest share of what is free (C
-    // itself comes later); the rest are rebuilt by the numeric kernel
-    store_rows = (int)std::min<double>((double)nbig, 0.15 * (double)free_b / (double)bm_bytes);
-    if (store_rows) B200_CUDA(dalloc(&d_bmstore, (size_t)store_rows * nw64));
+    // keep the bitmaps of the heaviest rows while they use a modest share of the memory (C
+    // itself comes later); the rest are rebuilt by the numeric kernel.  The store lives in the
+    // context and is re-used by later calls.
+    const size_t want_words = (size_t)nbig * nw64;
+    if (c.bm_store_words < want_words) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const size_t budget_words = (size_t)(0.15 * (double)(free_b + c.bm_store_words * 8)) / 8;
+      const size_t new_words = std::min(want_words, budget_words);
+      if (new_words > c.bm_store_words) {
+        B200_CUDA(cudaStreamSynchronize(st));
+        if (c.bm_store) cudaFree(c.bm_store);
+        c.bm_store = nullptr;
+        c.bm_store_words = 0;
+        if (cudaMalloc((void**)&c.bm_store, new_words * 8) == cudaSuccess) c.bm_store_words = new_words;
+        else cudaGetLastError();  // no store: every bitmap is rebuilt
+      }
+    }
+    store_rows = (int)std::min<size_t>((size_t)nbig, c.bm_store_words / (size_t)nw64);
+    d_bmstore = store_rows ? c.bm_store : nullptr;
     if (!sym_smem || !num_smem)
       B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     tick(2 * SB_BITMAP);
     sym_timed[SB_BITMAP] = true;
-    if (sym_smem) {
+    if (use_parts && !sym_smem) {  // (the whole-row kernel is a little faster when it fits)
+      // column-part boundaries inside every B row (shared with the numeric pass)
+      B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
+      if (nparts > 1) {
+        const long long nt = (long long)B.rows * (nparts - 1);
+        k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
+        ++launches;
+      }
+      const long long sitems = (long long)nbig * nparts;
+      const int sgrid = (int)std::min<long long>(sitems, (long long)part_ctas * c.sm_count);
+      const size_t ssm = walk_part_bytes + (size_t)wpp * 8;
+#define LAUNCH_SYM_PART(BTP, MINB)                                                              \
+  do {                                                                                          \
+    if ((rc = set_smem(k_sym_bitmap_part<BTP, MINB>, ssm))) return rc;                          \
+    k_sym_bitmap_part<BTP, MINB><<<sgrid, BTP, ssm, st>>>(                                      \
+        sb.d_list + sb.off[SB_BITMAP], nbig, nparts, wpp, row_lo, A.rowptr, A.col, A.val,       \
+        B.rowptr, B.col, nw64, d_bmstore, store_rows, d_bmslot, d_partcnt, d_bsplit, B.rows,    \
+        d_work + 0, l2m);                                                                       \
+  } while (0)
+      if (parts4) LAUNCH_SYM_PART(256, 4); else LAUNCH_SYM_PART(512, 2);
+#undef LAUNCH_SYM_PART
+      k_sum_parts<<<(nbig + 255) / 256, 256, 0, st>>>(sb.d_list + sb.off[SB_BITMAP], nbig, nparts,
+                                                      d_partcnt, d_cnt);
+      ++launches;
+    } else if (sym_smem) {
       if ((rc = set_smem(k_sym_bitmap<BT_BIG, true>, walk_bytes + bm_bytes))) return rc;
       k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, walk_bytes + bm_bytes, st>>>(
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
@@ -1899,13 +2016,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(dalloc(&d_ready, (size_t)nslots));
       B200_CUDA(cudaMemsetAsync(d_tsize + nslots, 0, sizeof(int), st));
       B200_CUDA(cudaMemsetAsync(d_ready, 0, (size_t)nslots * sizeof(int), st));
-      // column-part boundaries inside every B row
-      int* d_bsplit = nullptr;
-      B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
-      if (nparts > 1) {
-        const long long nt = (long long)B.rows * (nparts - 1);
-        k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
-        ++launches;
+      if (!d_bsplit) {  // no row went through the part-wise symbolic kernel
+        B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
+        if (nparts > 1) {
+          const long long nt = (long long)B.rows * (nparts - 1);
+          k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
+          ++launches;
+        }
       }
       const long long team_products = getenv("B200_TEAM_P") ? atoll(getenv("B200_TEAM_P")) : 98304;
       const int team_max = getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64;
@@ -1932,7 +2049,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   } while (0)
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
-      dfree(d_tsize); dfree(d_ready); dfree(d_bsplit);
+      dfree(d_tsize); dfree(d_ready);
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
@@ -2001,8 +2118,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     dfree(d_agg);
   }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
-  dfree(sb.d_list); dfree(nb.d_list); dfree(d_bmstore); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff);
+  dfree(sb.d_list); dfree(nb.d_list); dfree(d_gscr); dfree(d_work);
+  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff); dfree(d_bsplit);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {
@@ -2022,6 +2139,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->nnz_out = nnz_out;
     stats->nnz_unpruned = unpruned;
     stats->launches = launches;
+    stats->part_kernel = use_parts ? 1 : 0;
+    stats->part_count = nparts;
     for (int b = 0; b < 16; ++b) {
       stats->bins_rows[b] = nb.cnt[b];
       stats->sym_bin_rows[b] = sb.cnt[b];

@@ -180,9 +180,10 @@ def test_empty_operands(gpu):
     assert C.nnz == 0 and C.cols == 7
 
 
-def test_wide_matrix_uses_hbm_bitmap(gpu):
-    """More columns than the shared-memory bitmap holds (n > 1.8M): HBM bitmap variant."""
-    n = 2_500_000
+@pytest.mark.parametrize("n", [1_900_000, 2_500_000])
+def test_wide_matrix_uses_hbm_bitmap(gpu, n):
+    """More columns than one shared-memory bitmap holds: n = 1.9M runs the part-wise symbolic and
+    numeric kernels (4 column parts), n = 2.5M the HBM-bitmap variant."""
     rng = np.random.default_rng(3)
     k = 400
     # B: k rows, each ~60 columns spread over n
