@@ -229,6 +229,40 @@ def gpuRmclIter(maxIter, Mgt, Mt, eps=0.0):
     return out, iters.value, hist[:iters.value].copy()
 
 
+# ---- multi-GPU rMCL (one process per GPU; not in the reference) -----------------
+
+def comm_unique_id():
+    """b200_comm_unique_id: the 128-byte NCCL id, created on rank 0 and shipped by the host program."""
+    buf = C.create_string_buffer(128)
+    check(_lib.load().b200_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank, nranks, uid):
+    _ensure_init()
+    check(_lib.load().b200_comm_init(int(rank), int(nranks), C.create_string_buffer(uid, 128)))
+
+
+def comm_destroy():
+    check(_lib.load().b200_comm_destroy())
+
+
+def gpuRmclIterSharded(maxIter, dMgt, dMt, eps=0.0):
+    """b200_rmcl_iter_sharded: every rank holds Mgt and Mt (device); rank r computes the r-th
+    flops-balanced row block each iteration, the pruned blocks are all-gathered and chaos is
+    max-reduced.  dMt is replaced by the final Mt (sorted rows).  Returns
+    (iters_done, chaos_history, ms_per_iteration)."""
+    lib = _lib.load()
+    iters = C.c_int(0)
+    hist = np.zeros(max(1, maxIter), dtype=np.float64)
+    ms = np.zeros(max(1, maxIter), dtype=np.float64)
+    if not isinstance(dMt.handle, csr_t):
+        dMt.handle = csr_t(dMt.handle)
+    check(lib.b200_rmcl_iter_sharded(int(maxIter), float(eps), dMgt.handle, C.byref(dMt.handle),
+                                     C.byref(iters), _dp(hist), _dp(ms)))
+    return iters.value, hist[:iters.value].copy(), ms[:iters.value].copy()
+
+
 def rmclInit(rows_idx, cols_idx, n):
     """rmclInit (nlibs/qrmcl.cc:126-134) on a duplicate-free edge list: self loops, sorted rows,
     values 1/rowcount.  Input preparation on the host (numpy); not part of the timed path."""

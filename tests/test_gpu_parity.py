@@ -138,6 +138,22 @@ def test_rmcl_to_convergence(gpu):
     assert np.array_equal(ol.o_row_argmax(M_of(Mt)), ol.o_row_argmax(want))
 
 
+def test_sharded_loop_single_rank(gpu):
+    """b200_rmcl_iter_sharded with one rank (no collective): same iterates as the reference loop.
+    The 2-rank NCCL path is exercised by tools/run_sharded_rmcl.py under torchrun."""
+    A = gpu.synth_planted(4000, 20, 10, 2, 9)
+    want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 6)
+    ol.o_make_ordered(want)
+    dG, dT = A.toGpuCSR(), A.toGpuCSR()
+    iters, hist, ms = gpu.gpuRmclIterSharded(6, dG, dT)
+    got = dT.toCpuCSR()
+    dG.deviceDispose()
+    dT.deviceDispose()
+    assert iters == 6 and len(ms) == 6 and np.all(ms > 0)
+    ol.assert_same(M_of(got), want, TOL, "sharded loop, 1 rank")
+    assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
+
+
 def test_rectangular_unsorted_and_empty_rows(gpu):
     A = random_csr(gpu, 300, 200, 0.03, 1, empty_rows=0.2)
     B = random_csr(gpu, 200, 500, 0.05, 2, sort=False, empty_rows=0.1)
