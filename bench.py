@@ -12,8 +12,9 @@ row offsets → numeric (sorted columns), result left in HBM.
 * value       2·P·K / t, P = intermediate products (counted by the flops-analysis kernel), t =
               CUDA-event time of K steps on the library's stream, max over ranks; operands
               resident in HBM.  N > 1: the rows of A are cut into N contiguous blocks of equal
-              products (arrayEqualPartition64), rank r computes block r against the full B;
-              no collective on the data path; total work fixed => "scaling": "strong".
+              cost (arrayEqualPartition64 on products + a per-row charge), rank r computes
+              block r against the full B; no collective on the data path; total work fixed =>
+              "scaling": "strong".
 * e2e         the same product through the reference-facing host-buffer entry point
               b200_spgemm_csr (malloc'd int CSR in and out, include/b200_spgemm.h), H2D and
               D2H copies inside the timed region.  nnz(C) = 9.7e9 exceeds the reference's
@@ -74,6 +75,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="development: skip the CPU baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--row-charge", type=int, default=32768,
+                    help="products-equivalent fixed cost of a heavy row in the N>1 row partition")
     return ap.parse_args()
 
 
@@ -289,7 +292,15 @@ def run_b200(args):
     dA = A.toGpuCSR()
     prefix = smf.flops_prefix(dA, dA)
     P = int(prefix[-1])
-    ends = smf.arrayEqualPartition64(prefix, world)
+    # Row blocks of equal COST: products plus a fixed charge for every row that goes through the
+    # CTA-per-row bitmap kernels.  Equal products alone (the reference's thread partition,
+    # arrayEqualPartition64 on the flops prefix) leaves the rank that holds the long tail of
+    # lighter rows 1.7x slower than the rank that holds the hubs (measured at N=4: 50 / 63 / 75 /
+    # 84 ms per rank); a charge of 32K products per heavy row gives 69 / 68 / 67 / 67 ms.
+    per_row = np.diff(prefix)
+    cost = per_row + args.row_charge * (per_row > 512)
+    cost_prefix = np.concatenate([[0], np.cumsum(cost)]).astype(np.int64)
+    ends = smf.arrayEqualPartition64(cost_prefix, world)
     lo, hi = int(ends[rank]), int(ends[rank + 1])
 
     acc = {"sym": np.zeros(16), "num": np.zeros(16), "launches": 0, "last": None,
@@ -319,7 +330,11 @@ def run_b200(args):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total, float(acc["launches"])], dtype=torch.float64, device="cuda")
+    rank_ms = [ms_total / args.steps]
     if world > 1:
+        allms = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allms, t[:1].clone())
+        rank_ms = [float(x[0]) / args.steps for x in allms]
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -391,7 +406,8 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "rows": A.rows, "nnzA": A.nnz, "products": P, "nnzC": nnzC,
-                       "partition": "flops-balanced contiguous row blocks, 1 per GPU",
+                       "partition": "cost-balanced contiguous row blocks (products + %d per heavy row), 1 per GPU" % args.row_charge,
+                       "rank_ms_per_step": [round(x, 3) for x in rank_ms],
                        "l2": "no flush: inputs (%.0f MB) and output exceed the %d MB L2" % (
                            (12 * A.nnz + 8 * A.rows) / 1e6, L2_BYTES // (1024 * 1024))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
