@@ -1217,7 +1217,8 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
                   const int* __restrict__ bm_slot, const int* __restrict__ partcnt,
                   const int64_t* __restrict__ Crp, int* __restrict__ Ccol,
                   double* __restrict__ Cval, const int* __restrict__ itemoff,
-                  int* __restrict__ team_ready, const int* __restrict__ bsplit, int krows,
+                  const int* __restrict__ ticket_slot, int* __restrict__ team_ready,
+                  const int* __restrict__ bsplit, int krows,
                   int* __restrict__ work_counter, L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_red[BT / 32];
@@ -1247,14 +1248,7 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
     if (threadIdx.x == 0) {
       const int t = atomicAdd(work_counter, 1);
       s_idx = t;
-      if (t < tickets) {  // slot q with itemoff[q] <= t < itemoff[q+1]
-        int lo = 0, hi = nslots - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (itemoff[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        s_slot = lo;
-      }
+      if (t < tickets) s_slot = ticket_slot[t];  // slot q with itemoff[q] <= t < itemoff[q+1]
     }
     __syncthreads();
     const int t = s_idx;
@@ -1495,6 +1489,14 @@ k_sum_parts(const int* __restrict__ list, int count, int nparts, const int* __re
   int s = 0;
   for (int k = 0; k < nparts; ++k) s += partcnt[(size_t)i * PARTS_MAX + k];
   rownnz[i] = s;
+}
+
+// ticket -> slot table (one load per work item instead of a binary search over itemoff)
+__global__ void __launch_bounds__(256)
+k_fill_tickets(const int* __restrict__ itemoff, int nslots, int* __restrict__ ticket_slot) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nslots) return;
+  for (int t = itemoff[q]; t < itemoff[q + 1]; ++t) ticket_slot[t] = q;
 }
 
 // team size of every (row, part) slot of the part-wise numeric kernel: 0 for an empty part,
@@ -2036,7 +2038,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         cub::DeviceScan::ExclusiveSum(tmp, tb, d_tsize, d_itemoff, nslots + 1, st);
         cudaFreeAsync(tmp, st);
       }
-      launches += 2;
+      int* d_ticket_slot = nullptr;  // at most team_max tickets per slot, usually ~1.2 per slot
+      int h_tickets = 0;
+      B200_CUDA(cudaMemcpyAsync(&h_tickets, d_itemoff + nslots, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      B200_CUDA(dalloc(&d_ticket_slot, (size_t)h_tickets + 1));
+      k_fill_tickets<<<(nslots + 255) / 256, 256, 0, st>>>(d_itemoff, nslots, d_ticket_slot);
+      launches += 3;
       const int pgrid = part_ctas * c.sm_count;  // all resident: team members wait for each other
 
 #define LAUNCH_PART(BTP, MINB)                                                                  \
@@ -2044,12 +2052,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if ((rc = set_smem(k_num_bitmap_part<BTP, MINB>, part_smem))) return rc;                    \
     k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
         lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,     \
-        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_itemoff, d_ready,        \
-        d_bsplit, B.rows, d_work + 1, l2m);                                                     \
+        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_itemoff, d_ticket_slot,  \
+        d_ready, d_bsplit, B.rows, d_work + 1, l2m);                                            \
   } while (0)
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
-      dfree(d_tsize); dfree(d_ready);
+      dfree(d_tsize); dfree(d_ready); dfree(d_ticket_slot);
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
