@@ -15,11 +15,12 @@ row offsets → numeric (sorted columns), result left in HBM.
               cost (arrayEqualPartition64 on products + a per-row charge), rank r computes
               block r against the full B; no collective on the data path; total work fixed =>
               "scaling": "strong".
-* e2e         the same product through the reference-facing host-buffer entry point
-              b200_spgemm_csr (malloc'd int CSR in and out, include/b200_spgemm.h), H2D and
-              D2H copies inside the timed region.  nnz(C) = 9.7e9 exceeds the reference's
-              `int` CSR, so the caller walks row blocks (IA+lo, m=hi-lo) cut so
-              that every block's products (an upper bound of its nnz) fit an int.
+* e2e         the same product through the reference-facing call sequence with HOST buffers
+              (toGpuCSR -> gpuSpMMWrapper -> toCpuCSR: b200_csr_upload, b200_spgemm_device_rows,
+              b200_csr_download_rows; malloc'd int CSR in and out), H2D and D2H copies inside
+              the timed region.  nnz(C) = 9.7e9 exceeds the reference's `int` CSR, so the
+              caller walks row blocks cut so that every block's products (an upper bound of
+              its nnz) fit an int.
 * roofline    the kernel with the largest share of the step: algorithmic bytes of the rows it
               processed ÷ its CUDA-event duration (b200_stats.ms_*_bin), against the measured
               HBM copy bandwidth of MEASURED_PEAKS.json.
@@ -420,8 +421,12 @@ def run_b200(args):
 
 
 def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
-    """The reference-facing call with HOST buffers: b200_spgemm_csr per row block (IA+lo,
-    m=hi-lo), blocks cut on the host so that each block's product count fits an int."""
+    """The reference-facing call sequence with HOST buffers, every copy inside the timed region:
+    CSR::toGpuCSR (b200_csr_upload of the host matrix) -> gpuSpMMWrapper on row blocks
+    (b200_spgemm_device_rows) -> CSR::toCpuCSR of each block (b200_csr_download_rows: malloc'd
+    int CSR, freed by the caller) -> deviceDispose.  nnz(C) = 9.7e9 exceeds the reference's `int`
+    CSR, so the caller walks row blocks cut on the host so that each block's product count (an
+    upper bound of its nnz) fits an int."""
     from sparse_matrix_with_flops_b200 import _lib
     ip, dp = _lib.c_int_p, _lib.c_double_p
     prefix = host_flops_prefix(A)
@@ -429,27 +434,26 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     nblk = max(1, -(-mine // 2_000_000_000))
     local_prefix = (prefix[lo:hi + 1] - prefix[lo]).astype(np.int64)
     cuts = smf.arrayEqualPartition64(local_prefix, nblk) + lo
-    IA, JA, VA = A.rowPtr, A.colInd, A.values
     h2d = d2h = 0
 
     def one():
         nonlocal h2d, d2h
-        h2d = d2h = 0
+        dA = A.toGpuCSR()                                   # H2D: rowPtr, colInd, values
+        h2d = 4 * (A.rows + 1) + 12 * A.nnz
+        d2h = 0
         for b in range(nblk):
             r0, r1 = int(cuts[b]), int(cuts[b + 1])
             if r1 <= r0:
                 continue
+            dC = smf.gpuSpMMWrapper(dA, dA, r0, r1)
             IC, JC, Cv, nnzC = ip(), ip(), dp(), C.c_int(0)
-            ia = IA[r0:r1 + 1]  # a view: absolute offsets into JA / VA, as the reference allows
-            _lib.check(lib.b200_spgemm_csr(ia.ctypes.data_as(ip), JA.ctypes.data_as(ip),
-                                           VA.ctypes.data_as(dp), A.nnz, IA.ctypes.data_as(ip),
-                                           JA.ctypes.data_as(ip), VA.ctypes.data_as(dp), A.nnz,
-                                           C.byref(IC), C.byref(JC), C.byref(Cv), C.byref(nnzC),
-                                           r1 - r0, A.cols, A.cols))
-            h2d += 4 * (r1 - r0 + 1) + 12 * A.nnz + 4 * (A.rows + 1) + 12 * A.nnz
+            _lib.check(lib.b200_csr_download_rows(dC.handle, 0, r1 - r0, C.byref(IC), C.byref(JC),
+                                                  C.byref(Cv), C.byref(nnzC)))      # D2H
+            dC.deviceDispose()
             d2h += 4 * (r1 - r0 + 1) + 12 * nnzC.value
             for p in (IC, JC, Cv):
                 lib.b200_host_free(C.cast(p, C.c_void_p))
+        dA.deviceDispose()
 
     one()  # warm-up (page-faults the pools, loads the kernels)
     barrier()
@@ -469,7 +473,8 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     return {"value": 2.0 * P / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
             "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
             "warmup": 1, "row_blocks": nblk,
-            "api": "b200_spgemm_csr (host malloc'd int CSR in/out), wall clock incl. H2D + D2H"}
+            "api": "b200_csr_upload + b200_spgemm_device_rows + b200_csr_download_rows (host malloc'd int CSR "
+                   "in/out), wall clock incl. H2D + D2H"}
 
 
 def main():

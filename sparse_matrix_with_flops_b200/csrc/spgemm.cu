@@ -1830,7 +1830,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       cudaMemGetInfo(&free_b, &total_b);
       const size_t budget_words = (size_t)(0.15 * (double)(free_b + c.bm_store_words * 8)) / 8;
       const size_t new_words = std::min(want_words, budget_words);
-      if (new_words > c.bm_store_words) {
+      // grow only for a real gain: the budget moves a little from call to call with what else
+      // is allocated, and re-allocating tens of GB costs ~15 ms
+      if (new_words > c.bm_store_words + c.bm_store_words / 4) {
         B200_CUDA(cudaStreamSynchronize(st));
         if (c.bm_store) cudaFree(c.bm_store);
         c.bm_store = nullptr;
