@@ -788,6 +788,22 @@ __device__ __forceinline__ void walk_run_dynamic(const WalkSmem<BT>& ws, int nb,
       e = lo;
     }
     long long x = xb + lane;
+    // eight products in flight while they all lie in one B row (long rows: the common case)
+    for (; x + 224 < xe; x += 256) {
+      while (x >= ws.end[e]) ++e;
+      if (x + 224 >= ws.end[e]) break;
+      const long long base = ws.base[e] + x;
+      const double a = ws.a[e];
+      int col[8];
+      double bv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        col[u] = ldg_hint(Bcol + base + 32 * u, bpol);
+        if (WITH_VAL) bv[u] = ldg_hint(Bval + base + 32 * u, bpol);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f(col[u], WITH_VAL ? __dmul_rn(a, bv[u]) : 0.0);
+    }
     for (; x + 96 < xe; x += 128) {
       long long q[4];
       double av[4];
