@@ -18,17 +18,18 @@
 //    rounding as indexProcessCRowI, hence bit-identical values.  Because a B row has unique
 //    columns, a step never holds two products of the same column: no atomics are needed,
 //    insertion is a warp-synchronous write-then-verify;
-//  * large rows (more distinct columns than a shared-memory table holds): one CTA per row, a
-//    column bitmap in shared memory built with shared atomics in the symbolic pass and kept in
-//    HBM; the numeric pass turns it into rank = popcount-prefix, so the output row is produced
-//    directly in ascending column order and products are reduced with fp64 RED into the row's
-//    final location (order of additions not fixed: values agree to rounding, not bitwise);
-//  * output columns ascend in every row (in-shared-memory bitonic sort of packed
-//    (column,slot) keys for the hash bins; by construction for the bitmap bin);
+//  * large rows: a column BITMAP in shared memory indexes the accumulator,
+//    rank(c) = popcount prefix of the word + popcount of the bits below c, so the output row is
+//    produced directly in ascending column order.  Symbolic: CTA per row, test-then-atomicOr.
+//    Numeric (SpGEMM, sorted B): the columns of B are cut into parts of <= 8192 bitmap words,
+//    the work unit is a (row, part) slot handled by 512-thread CTAs (two per SM), heavy slots
+//    by a team of CTAs; the products are found with a flat, coalesced walk over the B-row
+//    segments of the part (k_bsplit table) and reduced with fp64 RED into the row's final slice
+//    of C.val (order of additions not fixed: values agree to rounding, not bitwise);
 //  * rMCL: inflation, row max/sum, threshold, prune, normalise and the chaos term are fused
-//    behind the numeric row while it is still on chip; pruned rows go to a bump-allocated
-//    arena and are gathered into the final CSR after a scan of the kept counts, so the
-//    unpruned product is never materialised in CSR form.
+//    behind the numeric row while it is still on chip (hash bins) or in a per-CTA scratch
+//    (bitmap bin); pruned rows go to a bump-allocated arena and are gathered into the final CSR
+//    after a scan of the kept counts, so the unpruned product is never materialised in CSR form.
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <vector>

@@ -264,3 +264,35 @@ def test_properties_at_scale(gpu):
     assert np.allclose(sums, 1.0, rtol=0, atol=1e-12)
     assert np.all(np.diff(Mt.colInd)[np.diff(rid) == 0] > 0)
     assert 0.0 <= chaos <= 1.0
+
+
+def test_cpp_host_layer(gpu, tmp_path):
+    """include/b200_nlibs.hpp (the C++ mirror of the reference's CSR / COO / PCSR / RMCL names)
+    compiled with g++ and run like one of the reference's one-main tests: all lines `Same`."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "shim_test.x")
+    lib = os.path.join(root, "sparse_matrix_with_flops_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "shim_test.cc"), "-o", exe,
+                           "-L" + lib, "-lb200spgemm", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "Diffs" not in out.stdout, out.stdout + out.stderr
+    assert out.stdout.count("Same") == 8
+
+
+def test_baseline_config_c1_nrmcl_rmat16(gpu):
+    """BASELINE.json configs[0]: rMCL (nrmcl, maxIters = 5) on symmetrised R-MAT scale 16, edge
+    factor 16 — the reference's own CPU-runnable case — against the checker at full size:
+    structure exact, values <= 1e-12 relative, chaos history equal, cluster labels exact."""
+    A = gpu.synth_rmat(16, 16, 12345, True)
+    want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 5)
+    ol.o_make_ordered(want)
+    Mt, iters, hist = gpu.gpuRmclIter(5, A, A)
+    assert iters == it_w == 5
+    ol.assert_same(M_of(Mt), want, TOL, "C1 nrmcl")
+    assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
+    d = Mt.toGpuCSR()
+    assert np.array_equal(d.row_argmax(), ol.o_row_argmax(want))
+    d.deviceDispose()

@@ -40,8 +40,10 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 traffic = {}
-with open(os.path.join(out, "%s_ncu_%s.csv" % (tag, workload)), "w") as f:
-    w = csv.writer(f); w.writerow(["kernel", "metric", "value", "unit"])
+mode = "a" if len(sys.argv) > 5 and sys.argv[5] == "append" else "w"
+with open(os.path.join(out, "%s_ncu_%s.csv" % (tag, workload)), mode) as f:
+    w = csv.writer(f)
+    if mode == "w": w.writerow(["kernel", "metric", "value", "unit"])
     for r in rr[2:]:
         kn = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("unnamed>::", "")
         rd = wr = 0.0
@@ -53,11 +55,14 @@ with open(os.path.join(out, "%s_ncu_%s.csv" % (tag, workload)), "w") as f:
                     if "read" in m: rd = v * scale
                     else: wr = v * scale
         base = kn.split("<")[0]
-        traffic[base] = int(rd + wr)
+        traffic[base] = int(rd + wr) if rd == rd and wr == wr and (rd + wr) > 0 else None
 tp = os.path.join(out, "traffic.json")
 allt = json.load(open(tp)) if os.path.exists(tp) else {}
-allt[workload] = traffic
+allt.setdefault(workload, {})
+for k, v in traffic.items():
+    if v is not None or k not in allt[workload]:
+        allt[workload][k] = v
 json.dump(allt, open(tp, "w"), indent=1)
 hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep, "22"], capture_output=True, text=True).stdout
-open(os.path.join(out, "%s_hot_lines_%s.txt" % (tag, workload)), "w").write(hot)
+open(os.path.join(out, "%s_hot_lines_%s.txt" % (tag, workload)), mode).write(hot)
 print("wrote profiles for", tag, workload, traffic)
