@@ -14,7 +14,8 @@
 //   static_omp_CSR_RMCL_OneStep        nlibs/cpu_csr_kernel.h:194-197
 //   gpuRmclIter, gpuSpMMWrapper        nlibs/gpus/gpu_csr_kernel.h:5-6
 //   rmclInit, RMCL, RunOptions         nlibs/qrmcl.h:8-24
-//   COO (in-memory part)               nlibs/COO.h:6-26
+//   COO (in-memory + readSNAPFile)     nlibs/COO.h:6-26, COO.cc:48-158,160-291
+//   Options, process_args              nlibs/process_args.{h,cc}
 //   PCSR                               nlibs/PCSR.h:5-101
 //
 // Error behaviour follows the reference: failures print the message and exit(EXIT_FAILURE)
@@ -25,6 +26,7 @@
 #define B200_NLIBS_HPP_
 
 #include <assert.h>
+#include <ctype.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -273,6 +275,76 @@ class COO {
     free(cooRowIndex); free(cooColIndex); free(cooVal);
     cooRowIndex = cooColIndex = NULL; cooVal = NULL;
   }
+  explicit COO(const char fname[]) : cooRowIndex(NULL), cooColIndex(NULL), cooVal(NULL), rows(0), cols(0), nnz(0) {
+    readSNAPFile(fname, false);
+  }
+  // Edge-list / MatrixMarket reader with the semantics of nlibs/COO.cc:48-158: leading lines
+  // that start with '#' or '%' are comments; a first line "%%MatrixMarket matrix coordinate
+  // <type> <symmetry>" makes the indices 1-based (and, for "symmetric", mirrors every
+  // off-diagonal entry); the first data line is "rows nnz" or "rows cols nnz"; every further
+  // line is "from to [value]" (value 1.0 when absent).  isTrans (the default, as rMCL works on
+  // the transposed flow matrix) swaps the endpoints of an unsymmetric file.
+  int readSNAPFile(const char fname[], bool isTrans = true) {
+    FILE* f = fopen(fname, "r");
+    if (!f) { printf("Failed to open file %s\n", fname); exit(-1); }
+    char line[1100];
+    bool isMtx = false, symmetric = false;
+    bool have = fgets(line, sizeof line, f) != NULL;
+    if (have && line[0] == '%') {
+      char t[5][128];
+      if (sscanf(line, "%127s %127s %127s %127s %127s", t[0], t[1], t[2], t[3], t[4]) == 5) {
+        isMtx = true;
+        for (char* q = t[4]; *q; ++q) *q = (char)tolower(*q);
+        symmetric = strcmp(t[4], "symmetric") == 0;
+      }
+    }
+    while (have && (line[0] == '#' || line[0] == '%')) have = fgets(line, sizeof line, f) != NULL;
+    if (!have) { nnz = 0; fclose(f); return 0; }
+    int f2 = 0, f3 = 0, declared = 0;
+    const int got = sscanf(line, "%d %d %d", &rows, &f2, &f3);
+    if (got == 2) { cols = rows; declared = f2; }
+    else { assert(got == 3); cols = f2; declared = f3; }
+    const size_t cap = (size_t)declared * (symmetric ? 2 : 1) + 1;
+    cooRowIndex = (int*)malloc(cap * sizeof(int));
+    cooColIndex = (int*)malloc(cap * sizeof(int));
+    cooVal = (QValue*)malloc(cap * sizeof(QValue));
+    if (!cooRowIndex || !cooColIndex || !cooVal) { fprintf(stderr, "malloc failed\n"); exit(EXIT_FAILURE); }
+    int top = 0;
+    for (int e = 0; e < declared; ++e) {
+      if (!fgets(line, sizeof line, f)) break;
+      int from, to;
+      double val = 1.0;
+      const int r = sscanf(line, "%d %d %lf", &from, &to, &val);
+      assert(r == 2 || r == 3);
+      if (r == 2) val = 1.0;
+      if (isMtx) { --from; --to; }
+      if (symmetric) {
+        cooRowIndex[top] = from; cooColIndex[top] = to; cooVal[top++] = val;
+        if (from != to) { cooRowIndex[top] = to; cooColIndex[top] = from; cooVal[top++] = val; }
+      } else {
+        cooRowIndex[top] = isTrans ? to : from;
+        cooColIndex[top] = isTrans ? from : to;
+        cooVal[top++] = val;
+      }
+    }
+    nnz = top;
+    fclose(f);
+    return 0;
+  }
+  // sort by (row, col) and drop repeated (row, col) pairs, keeping the first
+  // (nlibs/COO.cc:237-266); returns the number of entries removed
+  int orderedAndDuplicatesRemoving() {
+    makeOrdered();
+    int top = 0;
+    for (int e = 0; e < nnz; ++e) {
+      if (top && cooRowIndex[e] == cooRowIndex[top - 1] && cooColIndex[e] == cooColIndex[top - 1]) continue;
+      cooRowIndex[top] = cooRowIndex[e]; cooColIndex[top] = cooColIndex[e]; cooVal[top] = cooVal[e];
+      ++top;
+    }
+    const int removed = nnz - top;
+    nnz = top;
+    return removed;
+  }
   // one (i,i,1.0) entry for every vertex without a diagonal entry; input must be duplicate free
   // (SURVEY.md §8c input hazards)
   void addSelfLoopIfNeeded() {
@@ -336,6 +408,51 @@ inline CSR RMCL(COO& cooAt, int maxIters, RunOptions runOptions = B200, double e
   gpuRmclIter(maxIters, Mgt, Mt, eps, itersDone, NULL);
   Mgt.dispose();
   return Mt;
+}
+
+// RMCL from a file name, the reference's signature (nlibs/qrmcl.h:24, qrmcl.cc:136-164): the file
+// is read transposed, as the reference does (COO.cc:48 default isTrans = true)
+inline CSR RMCL(const char iname[], int maxIters, RunOptions runOptions = B200) {
+  COO cooAt;
+  cooAt.readSNAPFile(iname);
+  CSR Mt = RMCL(cooAt, maxIters, runOptions);
+  cooAt.dispose();
+  return Mt;
+}
+
+// ---- command line (nlibs/process_args.{h,cc}): the flags of the reference's drivers ----------
+struct Options {
+  char inputFileName[1024];
+  int maxIters;        // --maxIters / -m, default 5 (process_args.h:28)
+  int stride;          // --stride, default 512; accepted, unused on the device
+  RunOptions rmclOption;  // --rmclOptions / -r {SEQ,OMP,GPU,CILK,SOMP,MKL,SFOMP,HYB,B200}: all run the B200 path
+  bool stats, calcChange;
+  double eps;          // --eps: stationary-chaos stopping rule (not in the reference; 0 = fixed count)
+  Options() : maxIters(5), stride(512), rmclOption(B200), stats(false), calcChange(false), eps(0.0) { inputFileName[0] = 0; }
+};
+inline int process_args(int argc, char** argv, Options& options) {
+  static const char* names[] = {"SEQ", "OMP", "GPU", "CILK", "SOMP", "MKL", "SFOMP", "HYB", "B200"};
+  for (int a = 1; a < argc; ++a) {
+    const char* k = argv[a];
+    const char* v = (a + 1 < argc) ? argv[a + 1] : NULL;
+    auto is = [&](const char* l, const char* s_) { return !strcmp(k, l) || (s_ && !strcmp(k, s_)); };
+    if (is("--input", "-i") && v) { strncpy(options.inputFileName, v, sizeof(options.inputFileName) - 1); ++a; }
+    else if (is("--maxIters", "-m") && v) { options.maxIters = atoi(v); ++a; }
+    else if (is("--stride", NULL) && v) { options.stride = atoi(v); ++a; }
+    else if (is("--eps", NULL) && v) { options.eps = atof(v); ++a; }
+    else if (is("--rmclOptions", "-r") && v) {
+      for (int r = 0; r < 9; ++r) if (!strcmp(v, names[r])) options.rmclOption = (RunOptions)r;
+      ++a;
+    }
+    else if (is("--stats", "-s")) options.stats = true;
+    else if (is("--calcChange", "-c")) options.calcChange = true;
+    else if ((is("--shared", NULL) || is("--ptile", NULL) || is("--br", "-x") || is("--bc", "-y")) && v) ++a;  // accepted, no meaning here
+    else if (is("--help", "-h")) {
+      printf("usage: %s --input FILE [--maxIters N] [--rmclOptions B200] [--eps E] [--stride N] [--stats]\n", argv[0]);
+      return 1;
+    }
+  }
+  return 0;
 }
 
 // ---- PCSR: c column stripes of width ceil(cols/c) (nlibs/PCSR.h:5-101, PCSR.cc:3-56) -----------

@@ -2,6 +2,7 @@
 // drivers (nrmcl.cc:12-37 for rMCL, perfTests/only-somp.cc:24-37 for SpGEMM timing).  Host code
 // only: every computation goes through include/b200_nlibs.hpp -> libb200spgemm.so.
 //
+//   nrmcl_b200.x --input FILE [--maxIters N] [--rmclOptions B200] [--eps E]     (nrmcl.cc's flags)
 //   nrmcl_b200.x rmcl  <rmat|stencil|planted> <size> [maxIters] [eps]
 //   nrmcl_b200.x spmm  <rmat|stencil|planted> <size> [reps]
 //
@@ -29,7 +30,34 @@ static CSR make_input(const char* kind, int size, bool symmetrise) {
   return CSR(V, J, I, rows, rows, (int)nnz);
 }
 
+// nrmcl.cc:12-37 with the GPU path: RMCL(file), time, cluster count
+static int run_file(int argc, char* argv[]) {
+  Options options;
+  if (process_args(argc, argv, options)) return 0;
+  printf("input=%s maxIters=%d\n", options.inputFileName, options.maxIters);
+  double t0 = now_ms();
+  COO cooAt;
+  cooAt.readSNAPFile(options.inputFileName);
+  printf("rows=%d cols=%d nnz=%d\n", cooAt.rows, cooAt.cols, cooAt.nnz);
+  int iters = 0;
+  CSR Mt = RMCL(cooAt, options.maxIters, options.rmclOption, options.eps, &iters);
+  cooAt.dispose();
+  printf("time pass b200 rmcl total = %lf\n", now_ms() - t0);
+  std::set<int> attractors;
+  for (int i = 0; i < Mt.rows; ++i) {
+    int best = -1; double bv = 0.0;
+    for (int p = Mt.rowPtr[i]; p < Mt.rowPtr[i + 1]; ++p)
+      if (best < 0 || Mt.values[p] > bv) { best = Mt.colInd[p]; bv = Mt.values[p]; }
+    attractors.insert(best);
+  }
+  printf("iters %d final nnz %d clusters %zu\n", iters, Mt.nnz, attractors.size());
+  Mt.dispose();
+  b200_finalize();
+  return 0;
+}
+
 int main(int argc, char* argv[]) {
+  if (argc >= 2 && argv[1][0] == '-') return run_file(argc, argv);
   if (argc < 4) {
     fprintf(stderr, "usage: %s rmcl|spmm rmat|stencil|planted size [maxIters|reps] [eps]\n", argv[0]);
     return 2;

@@ -1,0 +1,23 @@
+// Host-only test of the C++ layer's ingest path (no GPU): COO::readSNAPFile -> rmclInit, printed
+// as plain text for tests/test_capi_cpu.py to compare with the golden vectors of the reference.
+#include "b200_nlibs.hpp"
+using namespace b200::nlibs;
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  COO coo;
+  coo.readSNAPFile(argv[1], atoi(argv[2]) != 0);
+  printf("coo %d %d %d\n", coo.rows, coo.cols, coo.nnz);
+  const int removed = coo.orderedAndDuplicatesRemoving();
+  printf("removed %d\n", removed);
+  for (int e = 0; e < coo.nnz; ++e) printf("e %d %d %.17g\n", coo.cooRowIndex[e], coo.cooColIndex[e], coo.cooVal[e]);
+  CSR M = rmclInit(coo);
+  printf("csr %d %d %d\n", M.rows, M.cols, M.nnz);
+  for (int i = 0; i <= M.rows; ++i) printf("p %d\n", M.rowPtr[i]);
+  for (int p = 0; p < M.nnz; ++p) printf("v %d %.17g\n", M.colInd[p], M.values[p]);
+  Options o;
+  const char* av[] = {"x", "-i", "some.snap", "--maxIters", "7", "-r", "SOMP", "--stride", "64", "-s"};
+  process_args(10, (char**)av, o);
+  printf("opts %s %d %d %d %d\n", o.inputFileName, o.maxIters, (int)o.rmclOption, o.stride, (int)o.stats);
+  M.dispose(); coo.dispose();
+  return 0;
+}

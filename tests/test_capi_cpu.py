@@ -91,3 +91,38 @@ def test_rmclinit_host_mirror_matches_oracle(smf, golden):
     m = smf.rmclInit(golden["t2_edges_r"], golden["t2_edges_c"], 3)
     assert np.array_equal(m.rowPtr, golden["t2_A_I"]) and np.array_equal(m.colInd, golden["t2_A_J"])
     assert np.array_equal(m.values, golden["t2_A_V"])
+
+
+def test_cpp_ingest_matches_reference_golden(golden, tmp_path):
+    """include/b200_nlibs.hpp: COO::readSNAPFile (edge list and symmetric MatrixMarket),
+    orderedAndDuplicatesRemoving, rmclInit and process_args — host code, compiled here with g++.
+    The t2 graph must give the rmclInit matrix the UNMODIFIED reference produced (golden t2_A)."""
+    import subprocess
+    exe = str(tmp_path / "ingest_test.x")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "ingest_test.cc"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "sparse_matrix_with_flops_b200"), "-lb200spgemm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "sparse_matrix_with_flops_b200")])
+
+    def run(path, trans):
+        out = subprocess.run([exe, path, str(trans)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        L = [ln.split() for ln in out.stdout.splitlines()]
+        return {"coo": [x for x in L if x[0] == "coo"][0], "removed": int([x for x in L if x[0] == "removed"][0][1]),
+                "I": np.array([int(x[1]) for x in L if x[0] == "p"], dtype=np.int32),
+                "J": np.array([int(x[1]) for x in L if x[0] == "v"], dtype=np.int32),
+                "V": np.array([float(x[2]) for x in L if x[0] == "v"]),
+                "edges": [(int(x[1]), int(x[2]), float(x[3])) for x in L if x[0] == "e"],
+                "opts": [x for x in L if x[0] == "opts"][0]}
+
+    t2 = run(os.path.join(ROOT, "tests", "golden", "t2_edges.snap"), 1)   # transposed, the reference's default
+    assert t2["coo"][1:] == ["3", "3", "4"] and t2["removed"] == 0
+    assert np.array_equal(t2["I"], golden["t2_A_I"]) and np.array_equal(t2["J"], golden["t2_A_J"])
+    assert np.array_equal(t2["V"].view(np.int64), golden["t2_A_V"].view(np.int64))
+    sym = run(os.path.join(ROOT, "tests", "golden", "sym4.mtx"), 1)
+    # 1-based, mirrored off-diagonals: (0,0) (1,0) (0,1) (2,1) (1,2) (3,3) (3,0) (0,3)
+    assert sorted((r, c) for r, c, _ in sym["edges"]) == [(0, 0), (0, 1), (0, 3), (1, 0), (1, 2), (2, 1), (3, 0), (3, 3)]
+    assert dict(((r, c), v) for r, c, v in sym["edges"])[(0, 3)] == 3.0
+    # rmclInit adds the missing self loops (vertices 1 and 2) and sets 1/rowcount
+    assert list(sym["I"]) == [0, 3, 6, 8, 10] and np.allclose(sym["V"][:3], 1 / 3)
+    assert t2["opts"][1:] == ["some.snap", "7", "4", "64", "1"]    # SOMP == 4 (nlibs/qrmcl.h:8)
