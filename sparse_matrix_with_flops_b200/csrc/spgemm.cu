@@ -56,6 +56,7 @@ constexpr int NB_W256 = 2;
 constexpr int NB_W1K = 3;
 constexpr int NB_W2K = 4;
 constexpr int NB_BITMAP = 5;
+constexpr int NB_W128 = 6;   // nnz(C_i) in (64, 128]: e.g. every interior row of a 27-point stencil
 
 // `big_from`: rows above this size go to the bitmap bin.  When the column bitmap of B fits in
 // shared memory it is the cheapest accumulator index for every row past the small warp tables
@@ -72,6 +73,7 @@ __host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_f
 __host__ __device__ inline int num_bin_of(int cnt, int big_from) {
   if (cnt == 0) return NB_NONE;
   if (cnt <= 64) return NB_W64;
+  if (cnt <= 128) return NB_W128;
   if (cnt <= 256) return NB_W256;
   if (cnt > big_from) return NB_BITMAP;
   if (cnt <= 1024) return NB_W1K;
@@ -303,38 +305,49 @@ __device__ __forceinline__ bool warp_find_or_insert(int* keys, int c, bool activ
 // symbolic, one warp per row, H key slots per warp (cRowiCount, cpu_csr_kernel.h:234-262)
 template <int H>
 __global__ void __launch_bounds__(256)
-k_sym_warp(const int* __restrict__ list, int count, int row_lo,
-           const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
+k_sym_warp(const int* __restrict__ list, int count, const int* __restrict__ count_dev,
+           int row_lo, const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
            const int64_t* __restrict__ Brp, const int* __restrict__ Bcol,
-           int* __restrict__ rownnz) {
+           int* __restrict__ rownnz, int limit, int* __restrict__ overflow_list,
+           int* __restrict__ overflow_count) {
+  // `limit` < H: OPTIMISTIC sizing.  A table sized for the products P_i (an upper bound of
+  // nnz(C_i)) costs 16 KB per warp for a 27-point stencil row (P = 729, nnz = 125) and leaves
+  // one 8-warp block per SM; instead the row is tried in a table a quarter of that size and
+  // handed to the next size up (overflow_list) only if it really has more than `limit` columns.
   extern __shared__ int smem_i[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (count_dev) count = *count_dev;   // retry pass: the list length lives on the device
   if (idx >= count) return;
   const int i = list[idx];
   int* keys = smem_i + warp * H;
   for (int k = lane; k < H; k += 32) keys[k] = EMPTY;
   __syncwarp();
   const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
-  int cnt = 0;
-  for (int64_t base = a0; base < a1; base += 32) {
+  int cnt = 0;  // warp-uniform
+  bool over = false;
+  for (int64_t base = a0; base < a1 && !over; base += 32) {
     const int64_t p = base + lane;
     long long bs = 0, be = 0;
     if (p < a1) { int j = __ldg(Acol + p); bs = __ldg(Brp + j); be = __ldg(Brp + j + 1); }
     const int nn = (int)min((int64_t)32, a1 - base);
-    for (int t = 0; t < nn; ++t) {
+    for (int t = 0; t < nn && !over; ++t) {
       const long long s = shfl64(bs, t), e = shfl64(be, t);
       for (long long q0 = s; q0 < e; q0 += 32) {
         const long long q = q0 + lane;
         const bool act = q < e;
         const int c = act ? __ldg(Bcol + q) : 0;
         unsigned h;
-        cnt += warp_find_or_insert<H>(keys, c, act, h) ? 1 : 0;
+        const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
+        cnt += __popc(__ballot_sync(FULL, isnew));
+        if (cnt > limit) { over = true; break; }   // the next step could fill the table
       }
     }
   }
-  cnt = warp_sum_int(cnt);
-  if (lane == 0) rownnz[i] = cnt;
+  if (lane == 0) {
+    if (over) overflow_list[atomicAdd(overflow_count, 1)] = i;
+    else rownnz[i] = cnt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1725,8 +1738,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const size_t bm_pref_bytes = bm_bytes + (((size_t)nw64 + 1) / 2) * 8;
   const size_t walk_bytes = sizeof(WalkSmem<BT_BIG>);
   const size_t smem_cap = c.smem_optin - 1024 - walk_bytes;  // static shared + the walk area
-  const bool sym_smem = bm_bytes <= smem_cap;
-  const bool num_smem = bm_pref_bytes <= smem_cap;
+  // B200_FORCE_WIDE=1 (testing switch): behave as if B had too many columns for any
+  // shared-memory bitmap, so small inputs exercise the big warp tables and the HBM bitmap
+  const bool force_wide = getenv("B200_FORCE_WIDE") != nullptr;
+  const bool sym_smem = !force_wide && bm_bytes <= smem_cap;
+  const bool num_smem = !force_wide && bm_pref_bytes <= smem_cap;
   // L2 eviction priorities of the bitmap kernels (B200_L2POL=acc,ocol,bgather,bmstore,demote
   // overrides them: a developer switch for A/B runs)
   L2Modes l2m = {L2_LAST, L2_FIRST, L2_NORMAL, L2_FIRST, 0};
@@ -1743,7 +1759,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const size_t part_smem = walk_part_bytes + (size_t)wpp * 12;
   const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && nparts <= PARTS_MAX &&
                          part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
-                         !getenv("B200_NO_PARTS");
+                         !getenv("B200_NO_PARTS") && !force_wide;
   if (!use_parts) { nparts = 1; wpp = nw64; }
   const long long sym_big_from = (sym_smem || use_parts) ? 512 : 8192;
   const int num_big_from = (num_smem || use_parts) ? 256 : 2048;
@@ -1799,24 +1815,53 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaEventRecord(c.ev[1], st));
 
   // ---- 2. symbolic per bin
-  auto launch_sym_warp = [&](int bin, auto kernel, int H, int WPB) -> int {
+  // warp-table bins; `Hopt`: optimistic table size tried first (0 = none), rows that overflow it
+  // are collected on the device and retried in the full-size table without a host round trip
+  int* d_over = nullptr;  // [0] overflow count per retry pass, then the lists
+  auto launch_sym_warp = [&](int bin, auto kernel_full, int H, int WPB, auto kernel_opt, int Hopt,
+                             int slot) -> int {
     const int cntb = sb.cnt[bin];
     if (!cntb) return B200_OK;
-    const size_t smem = (size_t)WPB * H * sizeof(int);
-    int r = set_smem(kernel, smem);
-    if (r) return r;
+    const int* lst = sb.d_list + sb.off[bin];
     tick(2 * bin);
-    kernel<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(sb.d_list + sb.off[bin], cntb, row_lo,
-                                                           A.rowptr, A.col, B.rowptr, B.col, d_cnt);
-    tick(2 * bin + 1);
     sym_timed[bin] = true;
-    ++launches;
+    if (Hopt) {
+      const int WO = 8;
+      const size_t so = (size_t)WO * Hopt * sizeof(int);
+      int r = set_smem(kernel_opt, so);
+      if (r) return r;
+      int* ocount = d_over + slot;
+      int* olist = d_over + 8 + (size_t)slot * m;
+      kernel_opt<<<(cntb + WO - 1) / WO, WO * 32, so, st>>>(lst, cntb, nullptr, row_lo, A.rowptr, A.col,
+                                                          B.rowptr, B.col, d_cnt, Hopt * 3 / 4 - 32,
+                                                          olist, ocount);
+      const size_t sf = (size_t)WPB * H * sizeof(int);
+      if ((r = set_smem(kernel_full, sf))) return r;
+      // grid sized for the worst case; warps beyond the overflow count exit at once
+      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, sf, st>>>(olist, cntb, ocount, row_lo, A.rowptr,
+                                                              A.col, B.rowptr, B.col, d_cnt, H,
+                                                              olist, ocount);
+      launches += 2;
+    } else {
+      const size_t smem = (size_t)WPB * H * sizeof(int);
+      int r = set_smem(kernel_full, smem);
+      if (r) return r;
+      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(lst, cntb, nullptr, row_lo, A.rowptr,
+                                                                A.col, B.rowptr, B.col, d_cnt, H,
+                                                                nullptr, nullptr);
+      ++launches;
+    }
+    tick(2 * bin + 1);
     return B200_OK;
   };
-  if ((rc = launch_sym_warp(SB_W256, k_sym_warp<256>, 256, 8))) return rc;
-  if ((rc = launch_sym_warp(SB_W1K, k_sym_warp<1024>, 1024, 8))) return rc;
-  if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8))) return rc;
-  if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3))) return rc;
+  if (sb.cnt[SB_W4K] || sb.cnt[SB_W16K]) {
+    B200_CUDA(dalloc(&d_over, (size_t)8 + 2 * (size_t)std::max(m, 1)));
+    B200_CUDA(cudaMemsetAsync(d_over, 0, 8 * sizeof(int), st));
+  }
+  if ((rc = launch_sym_warp(SB_W256, k_sym_warp<256>, 256, 8, k_sym_warp<256>, 0, 0))) return rc;
+  if ((rc = launch_sym_warp(SB_W1K, k_sym_warp<1024>, 1024, 8, k_sym_warp<1024>, 0, 0))) return rc;
+  if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8, k_sym_warp<1024>, 1024, 0))) return rc;
+  if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3, k_sym_warp<4096>, 4096, 1))) return rc;
 
   // large rows: bitmap
   unsigned long long* d_bmstore = nullptr;  // stored bitmaps of the symbolic bitmap bin
@@ -1997,11 +2042,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   };
   if (mode == MODE_SPGEMM) {
     if ((rc = launch_num_warp(NB_W64, k_num_warp<64, false>, 64, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W128, k_num_warp<128, false>, 128, 8))) return rc;
     if ((rc = launch_num_warp(NB_W256, k_num_warp<256, false>, 256, 8))) return rc;
     if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, false>, 1024, 8))) return rc;
     if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, false>, 2048, 4))) return rc;
   } else {
     if ((rc = launch_num_warp(NB_W64, k_num_warp<64, true>, 64, 8))) return rc;
+    if ((rc = launch_num_warp(NB_W128, k_num_warp<128, true>, 128, 8))) return rc;
     if ((rc = launch_num_warp(NB_W256, k_num_warp<256, true>, 256, 8))) return rc;
     if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, true>, 1024, 8))) return rc;
     if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, true>, 2048, 4))) return rc;
@@ -2146,7 +2193,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff); dfree(d_bsplit);
+  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff); dfree(d_bsplit); dfree(d_over);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {

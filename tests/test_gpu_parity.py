@@ -138,6 +138,20 @@ def test_rmcl_to_convergence(gpu):
     assert np.array_equal(ol.o_row_argmax(M_of(Mt)), ol.o_row_argmax(want))
 
 
+@pytest.mark.parametrize("name,make", SYNTH)
+def test_wide_fallback_paths(gpu, name, make, monkeypatch):
+    """B200_FORCE_WIDE=1 makes the library treat B as too wide for a shared-memory bitmap: the
+    optimistic / full-size warp tables (with the device-side overflow retry) and the HBM-bitmap
+    kernels then handle these inputs.  Same parity bar."""
+    monkeypatch.setenv("B200_FORCE_WIDE", "1")
+    A = make(gpu)
+    ol.assert_same(gpu_spgemm(gpu, A, A), want_spgemm(A, A), TOL, name + " wide")
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+    step = A.staticOmpRmclOneStep(A)
+    step.makeOrdered()
+    ol.assert_same(M_of(step), want1, TOL, name + " wide rMCL step")
+
+
 def test_sharded_loop_single_rank(gpu):
     """b200_rmcl_iter_sharded with one rank (no collective): same iterates as the reference loop.
     The 2-rank NCCL path is exercised by tools/run_sharded_rmcl.py under torchrun."""
