@@ -1324,11 +1324,29 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
     }
     const int w_lo = h * wpp, nwp = min(wpp, nw64 - w_lo);
     const int c_lo = w_lo * 64;
-    // first batch of A entries: segments located, B lines requested from L2 ahead of use
-    const int nb0 = (int)min((int64_t)BT, a1 - a0);
+    // How the team splits the products.  The A entries are walked in batches of BT; with at
+    // least as many batches as members (hub rows: 30 000 entries = 59 batches) member r takes
+    // whole batches r, r+T, ... — no member repeats another's batch preparation — otherwise
+    // the members are dealt round-robin to the batches and share a batch's flat index space.
+    const int nbat = (int)((a1 - a0 + BT - 1) / BT);
+    int b_first, b_step, sub_r, sub_T;
+    if (team_T >= nbat) {
+      b_first = team_r % nbat;
+      b_step = nbat;  // a single batch
+      sub_r = team_r / nbat;
+      sub_T = team_T / nbat + ((team_r % nbat) < (team_T % nbat) ? 1 : 0);
+    } else {
+      b_first = team_r;
+      b_step = team_T;
+      sub_r = 0;
+      sub_T = 1;
+    }
+    // this member's first batch: segments located, B lines requested from L2 ahead of use
+    const int64_t bf0 = a0 + (int64_t)b_first * BT;
+    const int nb0 = (int)min((int64_t)BT, a1 - bf0);
     const long long total0 =
-        walk_prepare_part<BT>(a0, nb0, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
-    walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval, team_r, team_T);
+        walk_prepare_part<BT>(bf0, nb0, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
+    walk_prefetch<BT, true>(ws, nb0, total0, Bcol, Bval, sub_r, sub_T);
     bool batch0_ready = true;
     // ---- the part's bitmap
     if (slotno >= 0) {
@@ -1337,8 +1355,8 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(bm);
       for (int w = threadIdx.x; w < (nwp >> 1); w += BT) dst2[w] = ldg_hint(src + w, pol_bm);
     } else {
-      build_part(h, true, total0);
-      batch0_ready = (a1 - a0) <= BT;  // the walk area still holds batch 0 only then
+      build_part(h, b_first == 0, total0);
+      batch0_ready = nbat == 1;  // the walk area still holds this member's first batch only then
     }
     __syncthreads();
     // ---- popcount prefix (lane = word), warp totals scanned across the CTA
@@ -1425,15 +1443,16 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
       }
       __syncthreads();
     }
-    for (int64_t b0 = a0; b0 < a1; b0 += BT) {
+    for (int bi = b_first; bi < nbat; bi += b_step) {
+      const int64_t b0 = a0 + (int64_t)bi * BT;
       const int nb = (int)min((int64_t)BT, a1 - b0);
       const long long total =
-          (batch0_ready && b0 == a0)
+          (batch0_ready && bi == b_first)
               ? total0
               : walk_prepare_part<BT>(b0, nb, Acol, Aval, Brp, bsplit, krows, h, nparts, ws);
       // this member's share of the batch, drawn by its warps in chunks
-      const long long per_member = (((total + team_T - 1) / team_T) + 31) & ~31LL;
-      const long long glo = min(total, (long long)team_r * per_member);
+      const long long per_member = (((total + sub_T - 1) / sub_T) + 31) & ~31LL;
+      const long long glo = min(total, (long long)sub_r * per_member);
       const long long ghi = min(total, glo + per_member);
       if (threadIdx.x == 0) s_next = glo;
       __syncthreads();
