@@ -275,6 +275,7 @@ int b200_finalize(void) {
   for (auto& ev : c.ev) { cudaEventDestroy(ev); ev = nullptr; }
   for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
   if (c.bm_store) { cudaFree(c.bm_store); c.bm_store = nullptr; c.bm_store_words = 0; }
+  c.bm_store_capped = false;
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   if (c.pin[0]) {

@@ -51,6 +51,7 @@ struct Ctx {
   // stream-ordered pool every call costs ~10 ms of remapping)
   unsigned long long* bm_store = nullptr;
   size_t bm_store_words = 0;
+  bool bm_store_capped = false;  // the last sizing was limited by the memory budget: do not retry
 };
 Ctx& ctx();
 

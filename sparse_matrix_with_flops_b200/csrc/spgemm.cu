@@ -1906,7 +1906,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     // itself comes later); the rest are rebuilt by the numeric kernel.  The store lives in the
     // context and is re-used by later calls.
     const size_t want_words = (size_t)nbig * nw64;
-    if (c.bm_store_words < want_words) {
+    // (cudaMemGetInfo costs ~20 ms of host time when the stream-ordered pool holds > 100 GB:
+    // once the store has been sized against the budget it is not re-examined)
+    if (c.bm_store_words < want_words && !c.bm_store_capped) {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
       const size_t budget_words = (size_t)(0.15 * (double)(free_b + c.bm_store_words * 8)) / 8;
@@ -1921,6 +1923,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         if (cudaMalloc((void**)&c.bm_store, new_words * 8) == cudaSuccess) c.bm_store_words = new_words;
         else cudaGetLastError();  // no store: every bitmap is rebuilt
       }
+      c.bm_store_capped = c.bm_store_words < want_words;
     }
     store_rows = (int)std::min<size_t>((size_t)nbig, c.bm_store_words / (size_t)nw64);
     d_bmstore = store_rows ? c.bm_store : nullptr;
