@@ -371,7 +371,7 @@ def run_b200(args):
     achieved = kb / (kms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:   # the ncu capture is of the whole product on one GPU
         traffic = json.load(open(tpath)).get(args.workload, {}).get(kname)
     nnzC = st["nnz_out"] if world == 1 else None
     step_bytes = None
