@@ -2115,7 +2115,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         }
       }
       const long long team_products = getenv("B200_TEAM_P") ? atoll(getenv("B200_TEAM_P")) : 98304;
-      const int team_max = getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64;
+      // a team must fit, with room to spare, among the CTAs that are resident at once (its
+      // members wait for each other): at most half of one CTA per SM
+      const int team_cap = std::max(1, c.sm_count / 2);
+      const int team_max =
+          std::min(team_cap, getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64);
       k_team_sizes<<<(nslots + 255) / 256, 256, 0, st>>>(lst, nbig_num, nparts, d_flops, d_partcnt,
                                                          team_products, team_max, d_tsize);
       {
