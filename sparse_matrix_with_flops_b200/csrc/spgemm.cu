@@ -882,6 +882,10 @@ __device__ __forceinline__ void bitmap_set(unsigned* bm32, int c) {
 }
 
 constexpr int PARTS_MAX = 4;  // column parts of the part-wise numeric kernel
+// column emission: a bitmap word with at least this many columns is expanded by the whole warp
+// (~14 instructions), a sparser one bit by bit by its own lane (~8 instructions per bit, for the
+// whole warp); 16 measured best on R-MAT 20 (8: -3 %)
+constexpr int DENSE_WORD = 16;
 
 // ------------------------------------------------------------------------------------------
 // symbolic for large rows: CTA per row (persistent, dynamic row fetch, heaviest rows first),
@@ -1070,7 +1074,7 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     int* ocol = RMCL ? scr_col + (size_t)blockIdx.x * scr_stride : Ccol + Crp[i];
     // The accumulators zeroed, and the columns in ascending order straight from the bitmap.
     // Groups of 32 words are dealt round-robin to the warps (the dense low-column region of a
-    // power-law row is shared by all of them), lane = word.  A dense word (>= 16 columns) is
+    // power-law row is shared by all of them), lane = word.  A dense word (>= DENSE_WORD columns) is
     // expanded by the whole warp — lane l tests bits l and l+32, the position is a popcount —
     // a sparse word by its own lane, bit by bit.  The positions of a group are consecutive
     // (pref[]), so either way a store instruction lands in a few adjacent sectors.
@@ -1082,7 +1086,7 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
         const int w = g * 32 + lane;
         unsigned long long x = (w < nw64) ? bm[w] : 0ull;
         int pos = (w < nw64) ? (int)pref[w] : 0;
-        const bool is_dense = __popcll(x) >= 16;
+        const bool is_dense = __popcll(x) >= DENSE_WORD;
         unsigned dense = __ballot_sync(FULL, is_dense);
         while (dense) {
           const int src = __ffs((int)dense) - 1;
@@ -1404,7 +1408,7 @@ k_num_bitmap_part(const int* __restrict__ list, int count, int nparts, int wpp, 
         const int w = g * 32 + lane;
         unsigned long long x = (w < nwp) ? bm[w] : 0ull;
         int pos = (w < nwp) ? (int)pref[w] : 0;
-        const bool is_dense = __popcll(x) >= 16;
+        const bool is_dense = __popcll(x) >= DENSE_WORD;
         unsigned dense = __ballot_sync(FULL, is_dense);
         while (dense) {
           const int src = __ffs((int)dense) - 1;
