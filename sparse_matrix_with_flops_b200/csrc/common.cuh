@@ -52,6 +52,12 @@ struct Ctx {
   unsigned long long* bm_store = nullptr;
   size_t bm_store_words = 0;
   bool bm_store_capped = false;  // the last sizing was limited by the memory budget: do not retry
+  // arena of the fused rMCL step (unpruned rows before compaction), grow-only between calls:
+  // its size changes every iteration and re-carving tens of GB out of the stream-ordered pool
+  // stalled single iterations for up to seconds
+  int* arena_col = nullptr;
+  double* arena_val = nullptr;
+  size_t arena_cap = 0;
 };
 Ctx& ctx();
 

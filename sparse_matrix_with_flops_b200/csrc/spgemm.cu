@@ -370,7 +370,6 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* sb, int n2
 struct RmclOut {          // where a fused rMCL row goes
   int* arena_col;
   double* arena_val;
-  unsigned long long* cursor;   // bump allocator over the arena
   long long* row_off;           // [m] arena offset of the row
   int* row_kept;                // [m] kept entries
   unsigned long long* chaos_bits;  // max over rows of (max - sum sq), as ordered bits
@@ -488,9 +487,9 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
     ksum = keep ? __dadd_rn(ksum, v) : ksum;
     kept += keep ? 1 : 0;
   }
-  unsigned long long off = 0;
-  if (lane == 0) off = atomicAdd(ro.cursor, (unsigned long long)kept);
-  off = (unsigned long long)shfl64((long long)off, 0);
+  // the row's slice of the arena is where its UNPRUNED product would start (Crp = offsets of
+  // the unpruned product): kept entries go to the front of it
+  const unsigned long long off = (unsigned long long)Crp[i];
   double sq_p = 0.0;
   int written = 0;
   for (int k0 = 0; k0 < cnt; k0 += 32) {
@@ -995,7 +994,6 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     if (prof && threadIdx.x == 0) { const long long t = clock64(); pc[k] += t - tprev; tprev = t; }
   };
   __shared__ int s_idx;
-  __shared__ unsigned long long s_off;
   // walk area, then bitmap words, then 32-bit exclusive popcount prefix per word
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm =
@@ -1150,9 +1148,7 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     }
     const double ksum = block_sum_d<BT>(ksum_p, s_redd);
     const int kept = block_sum_int<BT>(kept_p, s_red);
-    if (threadIdx.x == 0) s_off = atomicAdd(ro.cursor, (unsigned long long)kept);
-    __syncthreads();
-    const long long off = (long long)s_off;
+    const long long off = (long long)Crp[i];
     double sq_p = 0.0;
     int written = 0;
     for (int k0 = 0; k0 < cnt; k0 += BT) {
@@ -1601,6 +1597,79 @@ k_rmcl_empty_rows(const int* __restrict__ list, int count, RmclOut ro) {
   if (t < count) { ro.row_off[list[t]] = 0; ro.row_kept[list[t]] = 0; }
 }
 
+// rMCL epilogue of the rows whose unpruned product was written into their arena slice by the
+// part-wise numeric kernel (ascending columns): inflate, max / sum, threshold, prune,
+// normalise, chaos term (nlibs/tools/util.cc:4-69), in place — the kept entries are compacted
+// to the front of the slice.  One 256-thread CTA per row, persistent with dynamic fetch; sums
+// are fixed-shape (thread-strided partials, warp xor tree, ordered sum over warps), so the
+// result does not depend on scheduling.
+template <int BT>
+__global__ void __launch_bounds__(BT)
+k_rmcl_epilogue_rows(const int* __restrict__ list, int count, const int64_t* __restrict__ Crp,
+                     RmclOut ro, int* __restrict__ work_counter) {
+  __shared__ int s_red[BT / 32];
+  __shared__ double s_redd[BT / 32];
+  __shared__ int s_idx;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int idx = s_idx;
+    if (idx >= count) break;
+    const int i = list[idx];
+    const long long off = (long long)Crp[i];
+    const int cnt = (int)(Crp[i + 1] - off);
+    int* col = ro.arena_col + off;
+    double* acc = ro.arena_val + off;
+    double psum = 0.0, pmax = 0.0;
+    for (int k = threadIdx.x; k < cnt; k += BT) {
+      const double v = __ldcg(acc + k);  // written by RED at L2 in the previous kernel
+      const double v2 = __dmul_rn(v, v);
+      acc[k] = v2;
+      psum = __dadd_rn(psum, v2);
+      pmax = fmax(pmax, v2);
+    }
+    const double rsum = block_sum_d<BT>(psum, s_redd);
+    const double rmax = block_max_d<BT>(pmax, s_redd);
+    const double thresh = compute_threshold(__ddiv_rn(rsum, (double)cnt), rmax);
+    double ksum_p = 0.0;
+    int kept_p = 0;
+    for (int k = threadIdx.x; k < cnt; k += BT) {
+      const double v2 = acc[k];
+      if (v2 >= thresh) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
+    }
+    const double ksum = block_sum_d<BT>(ksum_p, s_redd);
+    const int kept = block_sum_int<BT>(kept_p, s_red);
+    double sq_p = 0.0;
+    int written = 0;
+    for (int k0 = 0; k0 < cnt; k0 += BT) {
+      const int k = k0 + threadIdx.x;
+      const double v2 = (k < cnt) ? acc[k] : 0.0;
+      const int c = (k < cnt) ? col[k] : 0;
+      const bool keep = (k < cnt) && (v2 >= thresh);
+      int tot;
+      // (the scan's barriers separate this chunk's reads from the writes below, which land at
+      // or before the positions just read: compaction only moves entries to the left)
+      const int ex = block_excl_scan<BT>(keep ? 1 : 0, s_red, &tot);
+      if (keep) {
+        const double w = __ddiv_rn(v2, ksum);
+        col[written + ex] = c;
+        acc[written + ex] = w;
+        sq_p = __dadd_rn(sq_p, __dmul_rn(w, w));
+      }
+      written += tot;
+    }
+    const double sq = block_sum_d<BT>(sq_p, s_redd);
+    if (threadIdx.x == 0) {
+      ro.row_off[i] = off;
+      ro.row_kept[i] = kept;
+      double ch = (kept > 0) ? __dsub_rn(__ddiv_rn(rmax, ksum), sq) : 0.0;
+      if (ch < 0.0) ch = 0.0;
+      atomicMax(ro.chaos_bits, (unsigned long long)__double_as_longlong(ch));
+    }
+  }
+}
+
 // gather pruned rows from the arena into the final CSR (omp_matrix_relocation,
 // nlibs/omp_csr_kernel.cc:201-236); one warp per row
 __global__ void __launch_bounds__(256)
@@ -1694,6 +1763,23 @@ int sort_rows_device(DevCSR* d) {
   return B200_OK;
 }
 
+// a column-sorted copy of (col, val) of `d` (row offsets shared); caller frees col2 / val2
+static int sorted_copy_device(const DevCSR& d, int** col2, double** val2) {
+  Ctx& c = ctx();
+  B200_CUDA(dalloc(col2, (size_t)d.nnz));
+  B200_CUDA(dalloc(val2, (size_t)d.nnz));
+  void* tmp = nullptr;
+  size_t tb = 0;
+  cub::DeviceSegmentedSort::SortPairs(nullptr, tb, d.col, *col2, d.val, *val2, d.nnz, d.rows,
+                                      d.rowptr, d.rowptr + 1, c.stream);
+  B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, c.stream));
+  cub::DeviceSegmentedSort::SortPairs(tmp, tb, d.col, *col2, d.val, *val2, d.nnz, d.rows,
+                                      d.rowptr, d.rowptr + 1, c.stream);
+  B200_CUDA(cudaGetLastError());
+  cudaFreeAsync(tmp, c.stream);
+  return B200_OK;
+}
+
 int check_sorted_device(DevCSR* d) {
   Ctx& c = ctx();
   d->sorted_rows = true;
@@ -1780,7 +1866,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int nparts = (nw64 + part_words_max - 1) / part_words_max;
   int wpp = (((nw64 + nparts - 1) / nparts) + 1023) & ~1023;  // a multiple of the sweep step of k_sym_bitmap
   const size_t part_smem = walk_part_bytes + (size_t)wpp * 12;
-  const bool use_parts = mode == MODE_SPGEMM && B.sorted_rows && nparts <= PARTS_MAX &&
+  // (rMCL mode too: the part kernel then writes the unpruned row into its arena slice and
+  // k_rmcl_epilogue_rows prunes it in place.  Unsorted B rows — an rMCL iterate in first-touch
+  // order — need a column-sorted copy of B when there is more than one part.)
+  const bool use_parts = nparts <= PARTS_MAX &&
                          part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
                          !getenv("B200_NO_PARTS") && !force_wide;
   if (!use_parts) { nparts = 1; wpp = nw64; }
@@ -1905,6 +1994,18 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const int nbig = sb.cnt[SB_BITMAP];
   int big_grid = std::min(nbig, c.sm_count);
   int store_rows = 0;
+  // the bitmap kernels read B through `Bs`: B itself, or a column-sorted copy of it when its
+  // rows are unsorted and have to be cut at column-part boundaries
+  DevCSR Bs = B;
+  int* d_bs_col = nullptr;
+  double* d_bs_val = nullptr;
+  if (use_parts && nparts > 1 && !B.sorted_rows && B.nnz > 0) {
+    if ((rc = sorted_copy_device(B, &d_bs_col, &d_bs_val))) return rc;
+    Bs.col = d_bs_col;
+    Bs.val = d_bs_val;
+    Bs.sorted_rows = true;
+    launches += 2;
+  }
   if (nbig) {
     // keep the bitmaps of the heaviest rows while they use a modest share of the memory (C
     // itself comes later); the rest are rebuilt by the numeric kernel.  The store lives in the
@@ -1940,7 +2041,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
       if (nparts > 1) {
         const long long nt = (long long)B.rows * (nparts - 1);
-        k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
+        k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(Bs.rowptr, Bs.col, Bs.rows, nparts, wpp, d_bsplit);
         ++launches;
       }
       const long long sitems = (long long)nbig * nparts;
@@ -1951,7 +2052,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if ((rc = set_smem(k_sym_bitmap_part<BTP, MINB>, ssm))) return rc;                          \
     k_sym_bitmap_part<BTP, MINB><<<sgrid, BTP, ssm, st>>>(                                      \
         sb.d_list + sb.off[SB_BITMAP], nbig, nparts, wpp, row_lo, A.rowptr, A.col, A.val,       \
-        B.rowptr, B.col, nw64, d_bmstore, store_rows, d_bmslot, d_partcnt, d_bsplit, B.rows,    \
+        Bs.rowptr, Bs.col, nw64, d_bmstore, store_rows, d_bmslot, d_partcnt, d_bsplit, B.rows,  \
         d_work + 0, l2m);                                                                       \
   } while (0)
       if (parts4) LAUNCH_SYM_PART(256, 4); else LAUNCH_SYM_PART(512, 2);
@@ -2013,7 +2114,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   RmclOut ro = {};
   int* d_arena_col = nullptr;
   double* d_arena_val = nullptr;
-  unsigned long long* d_cursor = nullptr;  // [0] bump cursor, [1] chaos bits
+  unsigned long long* d_cursor = nullptr;  // [0] unused, [1] chaos bits
   long long* d_rowoff = nullptr;
   int* d_kept = nullptr;
   int* d_scr_col = nullptr;
@@ -2026,19 +2127,34 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     B200_CUDA(dalloc(&C->col, (size_t)unpruned));
     B200_CUDA(dalloc(&C->val, (size_t)unpruned));
   } else {
-    B200_CUDA(dalloc(&d_arena_col, (size_t)unpruned));
-    B200_CUDA(dalloc(&d_arena_val, (size_t)unpruned));
+    if (c.arena_cap < (size_t)unpruned) {
+      B200_CUDA(cudaStreamSynchronize(st));
+      if (c.arena_col) { cudaFree(c.arena_col); cudaFree(c.arena_val); }
+      c.arena_col = nullptr; c.arena_val = nullptr; c.arena_cap = 0;
+      const size_t want = (size_t)unpruned + (size_t)unpruned / 8 + 1;
+      size_t got = want;
+      if (cudaMalloc((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
+          cudaMalloc((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
+        got = (size_t)unpruned + 1;  // without the head-room
+        B200_CUDA(cudaMalloc((void**)&c.arena_col, got * sizeof(int)));
+        B200_CUDA(cudaMalloc((void**)&c.arena_val, got * sizeof(double)));
+      }
+      c.arena_cap = got;
+    }
+    d_arena_col = c.arena_col;
+    d_arena_val = c.arena_val;
     B200_CUDA(dalloc(&d_cursor, 2));
     B200_CUDA(cudaMemsetAsync(d_cursor, 0, 2 * sizeof(unsigned long long), st));
     B200_CUDA(dalloc(&d_rowoff, (size_t)m));
     B200_CUDA(dalloc(&d_kept, (size_t)m + 1));
     ro.arena_col = d_arena_col;
     ro.arena_val = d_arena_val;
-    ro.cursor = d_cursor;
     ro.chaos_bits = d_cursor + 1;
     ro.row_off = d_rowoff;
     ro.row_kept = d_kept;
-    if (nbig_num) {
+    if (nbig_num && !use_parts) {
       scr_stride = n;  // a row has at most n distinct columns
       B200_CUDA(dalloc(&d_scr_col, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
       B200_CUDA(dalloc(&d_scr_val, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
@@ -2114,7 +2230,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
         if (nparts > 1) {
           const long long nt = (long long)B.rows * (nparts - 1);
-          k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(B.rowptr, B.col, B.rows, nparts, wpp, d_bsplit);
+          k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(Bs.rowptr, Bs.col, Bs.rows, nparts, wpp, d_bsplit);
           ++launches;
         }
       }
@@ -2147,12 +2263,21 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   do {                                                                                          \
     if ((rc = set_smem(k_num_bitmap_part<BTP, MINB>, part_smem))) return rc;                    \
     k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
-        lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,     \
-        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, C->col, C->val, d_itemoff, d_ticket_slot,  \
-        d_ready, d_bsplit, B.rows, d_work + 1, l2m);                                            \
+        lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, Bs.rowptr, Bs.col, Bs.val,  \
+        nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, out_col, out_val, d_itemoff,               \
+        d_ticket_slot, d_ready, d_bsplit, B.rows, d_work + 1, l2m);                             \
   } while (0)
+      // SpGEMM: straight into C; rMCL: the unpruned row into its arena slice, pruned in place by
+      // the epilogue kernel
+      int* out_col = mode == MODE_SPGEMM ? C->col : d_arena_col;
+      double* out_val = mode == MODE_SPGEMM ? C->val : d_arena_val;
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
+      if (mode == MODE_RMCL) {
+        const int egrid = std::min(nbig_num, c.sm_count * 8);
+        k_rmcl_epilogue_rows<256><<<egrid, 256, 0, st>>>(lst, nbig_num, d_urp, ro, d_work + 2);
+        ++launches;
+      }
       dfree(d_tsize); dfree(d_ready); dfree(d_ticket_slot);
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
@@ -2188,10 +2313,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     cudaFreeAsync(tmp, st);
     ++launches;
     unsigned long long h_cur[2] = {0, 0};
+    long long h_kept_total = 0;
     B200_CUDA(cudaMemcpyAsync(h_cur, d_cursor, 2 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(&h_kept_total, C->rowptr + m, sizeof(long long),
+                              cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    nnz_out = (long long)h_cur[0];
+    nnz_out = h_kept_total;
     if (chaos) {
       long long bits = (long long)h_cur[1];
       memcpy(chaos, &bits, sizeof(double));
@@ -2206,7 +2334,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       ++launches;
     }
     dfree(d_urp);
-    dfree(d_arena_col); dfree(d_arena_val); dfree(d_cursor); dfree(d_rowoff); dfree(d_kept);
+    dfree(d_cursor); dfree(d_rowoff); dfree(d_kept);
     dfree(d_scr_col); dfree(d_scr_val);
   }
   B200_CUDA(cudaEventRecord(c.ev[5], st));
@@ -2224,6 +2352,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
   dfree(sb.d_list); dfree(nb.d_list); dfree(d_gscr); dfree(d_work);
   dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff); dfree(d_bsplit); dfree(d_over);
+  dfree(d_bs_col); dfree(d_bs_val);
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
   if (stats) {

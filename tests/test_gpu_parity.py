@@ -229,6 +229,31 @@ def test_wide_matrix_uses_hbm_bitmap(gpu, n):
     ol.assert_same(gpu_spgemm(gpu, A, B), want_spgemm(A, B), TOL, "wide")
 
 
+def test_unsorted_b_with_two_column_parts(gpu):
+    """B has 600 K columns (two column parts) and UNSORTED rows, as an rMCL iterate in first-touch
+    order has: the part-wise kernels then work on a column-sorted copy of B.  SpGEMM and one
+    rMCL step against the checker."""
+    n, k = 600_000, 2000
+    rng = np.random.default_rng(21)
+    per = 300
+    cols = np.concatenate([rng.choice(n, size=per, replace=False) for _ in range(k)]).astype(np.int32)  # unsorted
+    rowPtr = (np.arange(k + 1) * per).astype(np.int32)
+    vals = rng.random(k * per) + 0.05
+    vals /= np.repeat(np.add.reduceat(vals, rowPtr[:-1]), per)        # row-stochastic, like Mt
+    B = gpu.CSR(vals, cols, rowPtr, k, n)
+    sizes = [1, 3, 2, 40, 7, 200, 15, 1000, 60, 2000, 5, 400]
+    arp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    acol = np.concatenate([np.sort(rng.choice(k, size=sz, replace=False)) for sz in sizes]).astype(np.int32)
+    aval = rng.random(len(acol)) + 0.1
+    A = gpu.CSR(aval, acol, arp, len(sizes), k)
+    ol.assert_same(gpu_spgemm(gpu, A, B), want_spgemm(A, B), TOL, "unsorted B, 2 parts")
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(B)))
+    step = A.staticOmpRmclOneStep(B)
+    step.makeOrdered()
+    ol.assert_same(M_of(step), want1, TOL, "unsorted B, 2 parts, rMCL step")
+    assert abs(step.chaos - ol.o_chaos(want1)) <= 1e-12
+
+
 def test_row_blocks_concatenate_to_the_whole(gpu):
     """SURVEY.md §7 hard part 1: row-block calls with flops-balanced cut points."""
     A = gpu.synth_rmat(11, 8, 5, True)
