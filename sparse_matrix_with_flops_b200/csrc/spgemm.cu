@@ -1873,7 +1873,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
                          part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
                          !getenv("B200_NO_PARTS") && !force_wide;
   if (!use_parts) { nparts = 1; wpp = nw64; }
-  const long long sym_big_from = (sym_smem || use_parts) ? 512 : 8192;
+  // symbolic cut: rows of up to 1024 products are cheaper in the (optimistically sized) warp
+  // tables at 56 warps / SM than as one bitmap item each (a 27-point stencil row has 729)
+  const long long sym_big_from = (sym_smem || use_parts) ? 1024 : 8192;
   const int num_big_from = (num_smem || use_parts) ? 256 : 2048;
 
   // ---- 1. flops analysis + symbolic binning
