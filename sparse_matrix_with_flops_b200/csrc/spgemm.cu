@@ -1881,7 +1881,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (!use_parts) { nparts = 1; wpp = nw64; }
   // symbolic cut: rows of up to 1024 products are cheaper in the (optimistically sized) warp
   // tables at 56 warps / SM than as one bitmap item each (a 27-point stencil row has 729)
-  const long long sym_big_from = (sym_smem || use_parts) ? 1024 : 8192;
+  long long sym_big_from = (sym_smem || use_parts) ? 1024 : 8192;
+  if (const char* e = getenv("B200_SYM_BIG_FROM")) sym_big_from = atoll(e);  // developer switch
   int num_big_from = (num_smem || use_parts) ? 256 : 2048;
   if (const char* e = getenv("B200_NUM_BIG_FROM")) num_big_from = atoi(e);  // developer switch
 
@@ -2139,9 +2140,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   } else {
     if (c.arena_cap < (size_t)unpruned) {
       B200_CUDA(cudaStreamSynchronize(st));
+      // head-room: an rMCL loop alternates between a few sizes, and re-allocating tens of GB
+      // costs ~1 s; grow by at least 2x the old capacity (falls back to the exact size below)
+      const size_t old_cap = c.arena_cap;
+      const size_t want = std::max((size_t)unpruned + (size_t)unpruned / 8 + 1, 2 * old_cap);
       if (c.arena_col) { cudaFree(c.arena_col); cudaFree(c.arena_val); }
       c.arena_col = nullptr; c.arena_val = nullptr; c.arena_cap = 0;
-      const size_t want = (size_t)unpruned + (size_t)unpruned / 8 + 1;
       size_t got = want;
       if (cudaMalloc((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
           cudaMalloc((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
