@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "b200_spgemm.h"
 
 namespace b200 {
@@ -98,6 +99,23 @@ inline bool rmcl_converged(double ch, double prev, int it, double eps) {
   const double d = ch > prev ? ch - prev : prev - ch;
   return ch < eps || (it > 0 && d < eps);
 }
+
+// Stream-ordered temporaries of one call: freed at scope exit, on the error paths too.  An
+// array that becomes part of the result is taken out with keep().
+struct Temps {
+  std::vector<void*> v;
+  template <typename T>
+  cudaError_t alloc(T** p, size_t count) {
+    const cudaError_t e = dalloc(p, count);
+    if (e == cudaSuccess) v.push_back((void*)*p);
+    return e;
+  }
+  void adopt(void* p) { if (p) v.push_back(p); }
+  void keep(const void* p) {
+    for (size_t k = 0; k < v.size(); ++k) if (v[k] == p) { v[k] = v.back(); v.pop_back(); return; }
+  }
+  ~Temps() { for (void* p : v) cudaFreeAsync(p, ctx().stream); }
+};
 
 // mode of the row pipeline
 enum Mode { MODE_SPGEMM = 0, MODE_RMCL = 1 };

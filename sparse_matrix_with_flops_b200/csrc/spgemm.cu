@@ -1839,6 +1839,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int launches = 0;
   if (stats) memset(stats, 0, sizeof(*stats));
   *C = DevCSR();
+  // on any early return the result is left empty (callers release it) and every temporary is
+  // freed: `out` is destroyed after `T`
+  struct OutGuard { DevCSR* C; bool ok; ~OutGuard() { if (!ok) *C = DevCSR(); } } out = {C, false};
+  Temps T;
   C->rows = m;
   C->cols = n;
   B200_CUDA(cudaEventRecord(c.ev[0], st));
@@ -1891,10 +1895,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   unsigned char* d_bin = nullptr;
   int* d_cnt = nullptr;
   long long* d_P = nullptr;
-  B200_CUDA(dalloc(&d_flops, (size_t)m));
-  B200_CUDA(dalloc(&d_bin, (size_t)m));
-  B200_CUDA(dalloc(&d_cnt, (size_t)m + 1));
-  B200_CUDA(dalloc(&d_P, 2));
+  B200_CUDA(T.alloc(&d_flops, (size_t)m));
+  B200_CUDA(T.alloc(&d_bin, (size_t)m));
+  B200_CUDA(T.alloc(&d_cnt, (size_t)m + 1));
+  B200_CUDA(T.alloc(&d_P, 2));
   if (m > 0) {
     k_row_flops<<<(unsigned)(((long long)m * 8 + 255) / 256), 256, 0, st>>>(
         A.rowptr, A.col, B.rowptr, row_lo, m, sym_big_from, d_flops, d_bin, d_cnt);
@@ -1911,6 +1915,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   Bins sb;
   int rc = make_bins(d_bin, m, &sb, &launches);
+  T.adopt(sb.d_list);
   if (rc) return rc;
   // heaviest rows first inside a bitmap bin: the persistent CTAs fetch rows dynamically, and a
   // hub row picked up last would be the tail of the kernel
@@ -1918,9 +1923,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if (count < 2) return B200_OK;
     long long *k0 = nullptr, *k1 = nullptr;
     int* l1 = nullptr;
-    B200_CUDA(dalloc(&k0, (size_t)count));
-    B200_CUDA(dalloc(&k1, (size_t)count));
-    B200_CUDA(dalloc(&l1, (size_t)count));
+    B200_CUDA(T.alloc(&k0, (size_t)count));
+    B200_CUDA(T.alloc(&k1, (size_t)count));
+    B200_CUDA(T.alloc(&l1, (size_t)count));
     k_gather_keys<<<(count + 255) / 256, 256, 0, st>>>(list, count, d_flops, k0);
     void* tmp = nullptr;
     size_t tb = 0;
@@ -1929,7 +1934,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     cub::DeviceRadixSort::SortPairsDescending(tmp, tb, k0, k1, list, l1, count, 0, 64, st);
     B200_CUDA(cudaMemcpyAsync(list, l1, (size_t)count * sizeof(int), cudaMemcpyDeviceToDevice, st));
     cudaFreeAsync(tmp, st);
-    dfree(k0); dfree(k1); dfree(l1);
+
     launches += 2;
     return B200_OK;
   };
@@ -1977,7 +1982,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     return B200_OK;
   };
   if (sb.cnt[SB_W4K] || sb.cnt[SB_W16K]) {
-    B200_CUDA(dalloc(&d_over, (size_t)8 + 2 * (size_t)std::max(m, 1)));
+    B200_CUDA(T.alloc(&d_over, (size_t)8 + 2 * (size_t)std::max(m, 1)));
     B200_CUDA(cudaMemsetAsync(d_over, 0, 8 * sizeof(int), st));
   }
   if ((rc = launch_sym_warp(SB_W256, k_sym_warp<256>, 256, 8, k_sym_warp<256>, 0, 0))) return rc;
@@ -1990,15 +1995,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   unsigned long long* d_gscr = nullptr;     // per-CTA bitmap(+prefix) scratch when not in smem
   int* d_bmslot = nullptr;                  // [m] slot in d_bmstore, or -1
   int* d_work = nullptr;
-  B200_CUDA(dalloc(&d_work, 4));
+  B200_CUDA(T.alloc(&d_work, 4));
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
-  B200_CUDA(dalloc(&d_bmslot, (size_t)m));
+  B200_CUDA(T.alloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
   int* d_bsplit = nullptr;   // column-part boundaries inside every B row (k_bsplit)
   int* d_itemoff = nullptr;  // ticket offsets of the (row, part) slots of k_num_bitmap_part
   int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
   if (use_parts) {
-    B200_CUDA(dalloc(&d_partcnt, (size_t)m * PARTS_MAX));
+    B200_CUDA(T.alloc(&d_partcnt, (size_t)m * PARTS_MAX));
     B200_CUDA(cudaMemsetAsync(d_partcnt, 0xff, (size_t)std::max(m, 1) * PARTS_MAX * sizeof(int), st));
   }
   const int nbig = sb.cnt[SB_BITMAP];
@@ -2010,7 +2015,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int* d_bs_col = nullptr;
   double* d_bs_val = nullptr;
   if (use_parts && nparts > 1 && !B.sorted_rows && B.nnz > 0) {
-    if ((rc = sorted_copy_device(B, &d_bs_col, &d_bs_val))) return rc;
+    rc = sorted_copy_device(B, &d_bs_col, &d_bs_val);
+    T.adopt(d_bs_col);
+    T.adopt(d_bs_val);
+    if (rc) return rc;
     Bs.col = d_bs_col;
     Bs.val = d_bs_val;
     Bs.sorted_rows = true;
@@ -2043,12 +2051,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     store_rows = (int)std::min<size_t>((size_t)nbig, c.bm_store_words / (size_t)nw64);
     d_bmstore = store_rows ? c.bm_store : nullptr;
     if (!sym_smem || !num_smem)
-      B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
+      B200_CUDA(T.alloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     tick(2 * SB_BITMAP);
     sym_timed[SB_BITMAP] = true;
     if (use_parts && !sym_smem) {  // (the whole-row kernel is a little faster when it fits)
       // column-part boundaries inside every B row (shared with the numeric pass)
-      B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
+      B200_CUDA(T.alloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
       if (nparts > 1) {
         const long long nt = (long long)B.rows * (nparts - 1);
         k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(Bs.rowptr, Bs.col, Bs.rows, nparts, wpp, d_bsplit);
@@ -2091,7 +2099,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
 
   // ---- 3. numeric binning, row offsets
   unsigned char* d_nbin = nullptr;
-  B200_CUDA(dalloc(&d_nbin, (size_t)m));
+  B200_CUDA(T.alloc(&d_nbin, (size_t)m));
   if (m > 0) {
     const long long light_p = getenv("B200_LIGHT_P") ? atoll(getenv("B200_LIGHT_P")) : 2560;
     k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p, d_nbin);
@@ -2099,7 +2107,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   B200_CUDA(cudaMemsetAsync(d_cnt + m, 0, sizeof(int), st));
   int64_t* d_urp = nullptr;  // offsets of the unpruned product (== C.rowptr for SpGEMM)
-  B200_CUDA(dalloc(&d_urp, (size_t)m + 1));
+  B200_CUDA(T.alloc(&d_urp, (size_t)m + 1));
   {
     cub::TransformInputIterator<long long, IntToI64, const int*> it(d_cnt, IntToI64());
     void* tmp = nullptr;
@@ -2115,6 +2123,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaMemcpyAsync(&h_tot[1], d_P, sizeof(long long), cudaMemcpyDeviceToHost, st));
   Bins nb;
   rc = make_bins(d_nbin, m, &nb, &launches);  // synchronises the stream
+  T.adopt(nb.d_list);
   if (rc) return rc;
   const long long unpruned = h_tot[0];
   const int nbig_num = nb.cnt[NB_BITMAP];
@@ -2135,8 +2144,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     C->rowptr = d_urp;
     C->nnz = unpruned;
     C->sorted_rows = true;
-    B200_CUDA(dalloc(&C->col, (size_t)unpruned));
-    B200_CUDA(dalloc(&C->val, (size_t)unpruned));
+    B200_CUDA(T.alloc(&C->col, (size_t)unpruned));
+    B200_CUDA(T.alloc(&C->val, (size_t)unpruned));
   } else {
     if (c.arena_cap < (size_t)unpruned) {
       B200_CUDA(cudaStreamSynchronize(st));
@@ -2159,10 +2168,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     }
     d_arena_col = c.arena_col;
     d_arena_val = c.arena_val;
-    B200_CUDA(dalloc(&d_cursor, 2));
+    B200_CUDA(T.alloc(&d_cursor, 2));
     B200_CUDA(cudaMemsetAsync(d_cursor, 0, 2 * sizeof(unsigned long long), st));
-    B200_CUDA(dalloc(&d_rowoff, (size_t)m));
-    B200_CUDA(dalloc(&d_kept, (size_t)m + 1));
+    B200_CUDA(T.alloc(&d_rowoff, (size_t)m));
+    B200_CUDA(T.alloc(&d_kept, (size_t)m + 1));
     ro.arena_col = d_arena_col;
     ro.arena_val = d_arena_val;
     ro.chaos_bits = d_cursor + 1;
@@ -2170,8 +2179,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ro.row_kept = d_kept;
     if (nbig_num && !use_parts) {
       scr_stride = n;  // a row has at most n distinct columns
-      B200_CUDA(dalloc(&d_scr_col, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
-      B200_CUDA(dalloc(&d_scr_val, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
+      B200_CUDA(T.alloc(&d_scr_col, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
+      B200_CUDA(T.alloc(&d_scr_val, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));
     }
     if (nb.cnt[NB_NONE]) {
       k_rmcl_empty_rows<<<(nb.cnt[NB_NONE] + 255) / 256, 256, 0, st>>>(nb.d_list + nb.off[NB_NONE],
@@ -2212,11 +2221,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (nbig_num) {
     const int grid = std::min(nbig_num, c.sm_count);
     if (!num_smem && !d_gscr)
-      B200_CUDA(dalloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
+      B200_CUDA(T.alloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     const int* lst = nb.d_list + nb.off[NB_BITMAP];
     unsigned long long* d_prof = nullptr;
     if (getenv("B200_PROF")) {
-      B200_CUDA(dalloc(&d_prof, 8));
+      B200_CUDA(T.alloc(&d_prof, 8));
       B200_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
     }
     tick(32 + 2 * NB_BITMAP);
@@ -2235,13 +2244,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       const int nslots = nbig_num * nparts;
       int* d_tsize = nullptr;
       int* d_ready = nullptr;
-      B200_CUDA(dalloc(&d_tsize, (size_t)nslots + 1));
-      B200_CUDA(dalloc(&d_itemoff, (size_t)nslots + 1));
-      B200_CUDA(dalloc(&d_ready, (size_t)nslots));
+      B200_CUDA(T.alloc(&d_tsize, (size_t)nslots + 1));
+      B200_CUDA(T.alloc(&d_itemoff, (size_t)nslots + 1));
+      B200_CUDA(T.alloc(&d_ready, (size_t)nslots));
       B200_CUDA(cudaMemsetAsync(d_tsize + nslots, 0, sizeof(int), st));
       B200_CUDA(cudaMemsetAsync(d_ready, 0, (size_t)nslots * sizeof(int), st));
       if (!d_bsplit) {  // no row went through the part-wise symbolic kernel
-        B200_CUDA(dalloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
+        B200_CUDA(T.alloc(&d_bsplit, (size_t)std::max(1, nparts - 1) * B.rows));
         if (nparts > 1) {
           const long long nt = (long long)B.rows * (nparts - 1);
           k_bsplit<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(Bs.rowptr, Bs.col, Bs.rows, nparts, wpp, d_bsplit);
@@ -2268,7 +2277,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       int h_tickets = 0;
       B200_CUDA(cudaMemcpyAsync(&h_tickets, d_itemoff + nslots, sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
-      B200_CUDA(dalloc(&d_ticket_slot, (size_t)h_tickets + 1));
+      B200_CUDA(T.alloc(&d_ticket_slot, (size_t)h_tickets + 1));
       k_fill_tickets<<<(nslots + 255) / 256, 256, 0, st>>>(d_itemoff, nslots, d_ticket_slot);
       launches += 3;
       const int pgrid = part_ctas * c.sm_count;  // all resident: team members wait for each other
@@ -2292,7 +2301,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         k_rmcl_epilogue_rows<256><<<egrid, 256, 0, st>>>(lst, nbig_num, d_urp, ro, d_work + 2);
         ++launches;
       }
-      dfree(d_tsize); dfree(d_ready); dfree(d_ticket_slot);
+
     } else if (num_smem) {
       if (mode == MODE_SPGEMM) LAUNCH_NUM_BM(true, false); else LAUNCH_NUM_BM(true, true);
     } else {
@@ -2307,7 +2316,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(cudaStreamSynchronize(st));
       fprintf(stderr, "[b200 prof] k_num_bitmap Mcycles/CTA: bitmap %.2f prefix %.2f emit %.2f products %.2f epilogue %.2f (grid %d)\n",
               h[0] / 1e6 / grid, h[1] / 1e6 / grid, h[2] / 1e6 / grid, h[3] / 1e6 / grid, h[4] / 1e6 / grid, grid);
-      dfree(d_prof);
+
     }
   }
   B200_CUDA(cudaGetLastError());
@@ -2317,7 +2326,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   long long nnz_out = unpruned;
   if (mode == MODE_RMCL) {
     B200_CUDA(cudaMemsetAsync(d_kept + m, 0, sizeof(int), st));
-    B200_CUDA(dalloc(&C->rowptr, (size_t)m + 1));
+    B200_CUDA(T.alloc(&C->rowptr, (size_t)m + 1));
     cub::TransformInputIterator<long long, IntToI64, const int*> it(d_kept, IntToI64());
     void* tmp = nullptr;
     size_t tb = 0;
@@ -2339,36 +2348,38 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       memcpy(chaos, &bits, sizeof(double));
     }
     C->nnz = nnz_out;
-    B200_CUDA(dalloc(&C->col, (size_t)nnz_out));
-    B200_CUDA(dalloc(&C->val, (size_t)nnz_out));
+    B200_CUDA(T.alloc(&C->col, (size_t)nnz_out));
+    B200_CUDA(T.alloc(&C->val, (size_t)nnz_out));
     if (m > 0) {
       const long long threads = (long long)m * 32;
       k_gather_rows<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
           m, d_rowoff, C->rowptr, d_arena_col, d_arena_val, C->col, C->val);
       ++launches;
     }
-    dfree(d_urp);
-    dfree(d_cursor); dfree(d_rowoff); dfree(d_kept);
-    dfree(d_scr_col); dfree(d_scr_val);
+
+
   }
   B200_CUDA(cudaEventRecord(c.ev[5], st));
   unsigned long long h_agg[96] = {0};
   if (stats && m > 0) {
     unsigned long long* d_agg = nullptr;
-    B200_CUDA(dalloc(&d_agg, 96));
+    B200_CUDA(T.alloc(&d_agg, 96));
     B200_CUDA(cudaMemsetAsync(d_agg, 0, 96 * sizeof(unsigned long long), st));
     const int grid = std::min((m + 255) / 256, c.sm_count * 8);
     k_bin_aggregate<<<grid, 256, 0, st>>>(d_bin, m, A.rowptr, row_lo, d_flops, nullptr, d_agg);
     k_bin_aggregate<<<grid, 256, 0, st>>>(d_nbin, m, A.rowptr, row_lo, d_flops, d_cnt, d_agg + 48);
     B200_CUDA(cudaMemcpyAsync(h_agg, d_agg, sizeof h_agg, cudaMemcpyDeviceToHost, st));
-    dfree(d_agg);
+
   }
-  dfree(d_flops); dfree(d_bin); dfree(d_cnt); dfree(d_P); dfree(d_nbin);
-  dfree(sb.d_list); dfree(nb.d_list); dfree(d_gscr); dfree(d_work);
-  dfree(d_bmslot); dfree(d_partcnt); dfree(d_itemoff); dfree(d_bsplit); dfree(d_over);
-  dfree(d_bs_col); dfree(d_bs_val);
+
+
+
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaGetLastError());
+  T.keep(C->rowptr);
+  T.keep(C->col);
+  T.keep(C->val);
+  out.ok = true;
   if (stats) {
     float t01, t12, t23, t34, t45, t05;
     cudaEventElapsedTime(&t01, c.ev[0], c.ev[1]);
