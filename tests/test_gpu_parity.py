@@ -335,3 +335,24 @@ def test_baseline_config_c1_nrmcl_rmat16(gpu):
     d = Mt.toGpuCSR()
     assert np.array_equal(d.row_argmax(), ol.o_row_argmax(want))
     d.deviceDispose()
+
+
+def test_error_behaviour(gpu):
+    """Error convention of the C ABI: a dimension mismatch (the reference asserts,
+    nlibs/CSR.cc:183) and an out-of-range row block come back as error codes with a message, and
+    leave the library usable."""
+    import ctypes as C
+    lib = gpu._lib.load()
+    A = gpu.synth_rmat(6, 4, 1, True)                      # 64 x 64
+    Bad = gpu.CSR(np.ones(3), np.array([0, 1, 2], dtype=np.int32), np.array([0, 1, 2, 3], dtype=np.int32), 3, 5)
+    dA, dB = A.toGpuCSR(), Bad.toGpuCSR()
+    h = gpu._lib.csr_t()
+    rc = lib.b200_spgemm_device(dA.handle, dB.handle, C.byref(h), None)
+    assert rc == 1 and b"dimension mismatch" in lib.b200_last_error()       # B200_ERR_BAD_ARG
+    rc = lib.b200_spgemm_device_rows(dA.handle, dA.handle, 10, 5, C.byref(h), None)
+    assert rc == 1 and b"row range" in lib.b200_last_error()
+    with pytest.raises(AssertionError):
+        A.flops_spmm(Bad)                                   # the Python mirror asserts like the reference
+    ok = gpu.gpuSpMMWrapper(dA, dA)                         # still works afterwards
+    assert ok.nnz > 0
+    ok.deviceDispose(); dA.deviceDispose(); dB.deviceDispose()
