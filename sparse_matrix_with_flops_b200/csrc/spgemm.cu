@@ -886,7 +886,9 @@ __device__ __forceinline__ void bitmap_set(unsigned* bm32, int c) {
   if (!(*(volatile unsigned*)w & bit)) atomicOr(w, bit);
 }
 
-constexpr int PARTS_MAX = 4;  // column parts of the part-wise numeric kernel
+constexpr int PARTS_MAX = 16;   // column parts of the part-wise kernels (16 x 512 K columns = 8 M)
+constexpr int PARTS_WHOLE = 4;  // ... of which the whole-row symbolic kernel can see at most 4
+                                // (its bitmap holds <= 1.8 M columns)
 // column emission: a bitmap word with at least this many columns is expanded by the whole warp
 // (~14 instructions), a sparser one bit by bit by its own lane (~8 instructions per bit, for the
 // whole warp); 16 measured best on R-MAT 20 (8: -3 %)
@@ -908,7 +910,7 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
              int nparts, int wpp, int* __restrict__ partcnt, int* __restrict__ work_counter,
              L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_pc[BT / 32][PARTS_MAX];
+  __shared__ int s_pc[BT / 32][PARTS_WHOLE];
   __shared__ int s_idx;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
@@ -929,7 +931,7 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
                                  [&](int c, double) { bitmap_set(bm32, c); });
     // count (per column part, see k_num_bitmap_part), store and clear in one sweep; wpp is a
     // multiple of BT, so the part of a sweep step is the same for the whole CTA
-    int pc[PARTS_MAX] = {0, 0, 0, 0};
+    int pc[PARTS_WHOLE] = {0, 0, 0, 0};
     unsigned long long* dst = (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 : nullptr;
     for (int w0 = 0, h = 0, hnext = wpp; w0 < nw64; w0 += BT) {
       const int w = w0 + threadIdx.x;
@@ -938,7 +940,7 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
         const unsigned long long x = bm[w];
         const int c = __popcll(x);
 #pragma unroll
-        for (int k = 0; k < PARTS_MAX; ++k) pc[k] += (k == h) ? c : 0;
+        for (int k = 0; k < PARTS_WHOLE; ++k) pc[k] += (k == h) ? c : 0;
         if (dst) stg_hint(dst + w, x, pol_bm);
         bm[w] = 0ull;
       }
@@ -946,24 +948,24 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
     {
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-      for (int k = 0; k < PARTS_MAX; ++k) pc[k] = warp_sum_int(pc[k]);
+      for (int k = 0; k < PARTS_WHOLE; ++k) pc[k] = warp_sum_int(pc[k]);
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < PARTS_MAX; ++k) s_pc[warp][k] = pc[k];
+        for (int k = 0; k < PARTS_WHOLE; ++k) s_pc[warp][k] = pc[k];
       }
       __syncthreads();
     }
     int cnt = 0;
     if (threadIdx.x == 0) {
-      int tot[PARTS_MAX] = {0, 0, 0, 0};
+      int tot[PARTS_WHOLE] = {0, 0, 0, 0};
       for (int wq = 0; wq < BT / 32; ++wq)
 #pragma unroll
-        for (int k = 0; k < PARTS_MAX; ++k) tot[k] += s_pc[wq][k];
+        for (int k = 0; k < PARTS_WHOLE; ++k) tot[k] += s_pc[wq][k];
 #pragma unroll
-      for (int k = 0; k < PARTS_MAX; ++k) cnt += tot[k];
+      for (int k = 0; k < PARTS_WHOLE; ++k) cnt += tot[k];
       if (partcnt)
 #pragma unroll
-        for (int k = 0; k < PARTS_MAX; ++k) partcnt[(size_t)i * PARTS_MAX + k] = tot[k];
+        for (int k = 0; k < PARTS_WHOLE; ++k) partcnt[(size_t)i * PARTS_MAX + k] = tot[k];
     }
     if (threadIdx.x == 0) {
       rownnz[i] = cnt;
@@ -1829,6 +1831,22 @@ int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi
   return B200_OK;
 }
 
+// cudaMalloc for the context's long-lived buffers; on failure the stream-ordered pool (which
+// keeps every freed block, e.g. a 100 GB result of an earlier call) is trimmed and the
+// allocation retried once
+static cudaError_t malloc_with_trim(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) return e;
+  cudaGetLastError();
+  Ctx& c = ctx();
+  cudaStreamSynchronize(c.stream);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) cudaGetLastError();
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------
 int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode, DevCSR* C,
                  double* chaos, b200_stats* stats) {
@@ -2043,8 +2061,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         if (c.bm_store) cudaFree(c.bm_store);
         c.bm_store = nullptr;
         c.bm_store_words = 0;
-        if (cudaMalloc((void**)&c.bm_store, new_words * 8) == cudaSuccess) c.bm_store_words = new_words;
-        else cudaGetLastError();  // no store: every bitmap is rebuilt
+        if (malloc_with_trim((void**)&c.bm_store, new_words * 8) == cudaSuccess) c.bm_store_words = new_words;
+        // else no store: every bitmap is rebuilt
       }
       c.bm_store_capped = c.bm_store_words < want_words;
     }
@@ -2160,9 +2178,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
           cudaMalloc((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
-        got = (size_t)unpruned + 1;  // without the head-room
-        B200_CUDA(cudaMalloc((void**)&c.arena_col, got * sizeof(int)));
-        B200_CUDA(cudaMalloc((void**)&c.arena_val, got * sizeof(double)));
+        got = (size_t)unpruned + 1;  // without the head-room, and with the pool trimmed if needed
+        if (malloc_with_trim((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
+            malloc_with_trim((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
+          if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
+          c.arena_val = nullptr;
+          set_error("out of device memory for the rMCL arena (unpruned product of this row block); "
+                    "shard the rows over more GPUs or call the *_rows entry points on smaller blocks");
+          return B200_ERR_CUDA;
+        }
       }
       c.arena_cap = got;
     }

@@ -15,6 +15,7 @@ for c in cases:
     elif c == "stencil128": A = smf.synth_stencil27(128, 128, 128)
     elif c == "planted": A = smf.synth_planted(400000, 100, 16, 2, 12345)
     elif c == "planted1m": A = smf.synth_planted(1000000, 1000, 16, 2, 12345)
+    elif c == "planted4m": A = smf.synth_planted(4000000, 1000, 16, 2, 12345)
     else: raise SystemExit(c)
     print(c, "rows", A.rows, "nnz", A.nnz, "gen %.1fs" % (time.time() - t0), flush=True)
     dA = A.toGpuCSR()
