@@ -28,7 +28,8 @@ row offsets → numeric (sorted columns), result left in HBM.
               the UNMODIFIED reference flops_omp_CSR_SpMM (oracle/_ref/libref.so, built by
               oracle/Makefile from /root/reference) — or the C restatement oracle/liboracle.so
               when that file is absent — on all host cores, on a bounded row sample of the same
-              product (every q-th row of A against the full B).
+              product (a hashed 1/q of the rows of A against the full B; the sample's product
+              count fits the reference's `int` CSR).
 
 Nothing on the measured GPU path touches oracle/.
 """
