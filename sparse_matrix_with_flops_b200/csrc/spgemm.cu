@@ -70,16 +70,18 @@ __host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_f
   if (P <= 2048) return SB_W4K;
   return SB_W16K;
 }
-// `light_p`: with the bitmap available, a row of up to 1024 columns still goes to the 1024-entry
-// warp table when it has few products — the bitmap item costs ~20 us of fixed work per (row,
+// `light_p`: with the bitmap available, a row of up to 2048 columns still goes to the 1024- or
+// 2048-entry warp table when it has few products — the bitmap item costs ~20 us of fixed work per (row,
 // part), the big warp table ~0.1 us per product at its 8 warps / SM: measured crossover on
 // planted-partition rows ~2.5 K products.
-__host__ __device__ inline int num_bin_of(int cnt, int big_from, long long P, long long light_p) {
+__host__ __device__ inline int num_bin_of(int cnt, int big_from, long long P, long long light_p,
+                                          long long light2k_p) {
   if (cnt == 0) return NB_NONE;
   if (cnt <= 64) return NB_W64;
   if (cnt <= 128) return NB_W128;
   if (cnt <= 256) return NB_W256;
   if (cnt <= 1024 && P <= light_p) return NB_W1K;
+  if (cnt <= 2048 && P <= light2k_p) return NB_W2K;  // only with > 2 column parts (measured)
   if (cnt > big_from) return NB_BITMAP;
   if (cnt <= 1024) return NB_W1K;
   return NB_W2K;
@@ -226,9 +228,9 @@ k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
 
 __global__ void __launch_bounds__(256)
 k_num_bins(const int* __restrict__ rownnz, const long long* __restrict__ flops, int m, int big_from,
-           long long light_p, unsigned char* __restrict__ nbin) {
+           long long light_p, long long light2k_p, unsigned char* __restrict__ nbin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p);
+  if (i < m) nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p, light2k_p);
 }
 
 // histogram of bin ids (<= 16 bins)
@@ -1903,7 +1905,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (!use_parts) { nparts = 1; wpp = nw64; }
   // symbolic cut: rows of up to 1024 products are cheaper in the (optimistically sized) warp
   // tables at 56 warps / SM than as one bitmap item each (a 27-point stencil row has 729)
-  long long sym_big_from = (sym_smem || use_parts) ? 1024 : 8192;
+  // (with more than two column parts a bitmap row costs one item per part it touches, and the
+  // cut moves up: measured on a 4 M-column planted-partition graph, 8 parts: 785 -> 243 ms)
+  long long sym_big_from = (sym_smem || use_parts) ? (nparts > 2 ? 4096 : 1024) : 8192;
   if (const char* e = getenv("B200_SYM_BIG_FROM")) sym_big_from = atoll(e);  // developer switch
   int num_big_from = (num_smem || use_parts) ? 256 : 2048;
   if (const char* e = getenv("B200_NUM_BIG_FROM")) num_big_from = atoi(e);  // developer switch
@@ -2119,8 +2123,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   unsigned char* d_nbin = nullptr;
   B200_CUDA(T.alloc(&d_nbin, (size_t)m));
   if (m > 0) {
-    const long long light_p = getenv("B200_LIGHT_P") ? atoll(getenv("B200_LIGHT_P")) : 2560;
-    k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p, d_nbin);
+    const long long light_p = getenv("B200_LIGHT_P") ? atoll(getenv("B200_LIGHT_P"))
+                                                     : 2560LL * std::max(1, nparts / 2);
+    k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p,
+                                                nparts > 2 ? light_p : 0, d_nbin);
     ++launches;
   }
   B200_CUDA(cudaMemsetAsync(d_cnt + m, 0, sizeof(int), st));
