@@ -14,6 +14,16 @@ int main(int argc, char** argv) {
   printf("csr %d %d %d\n", M.rows, M.cols, M.nnz);
   for (int i = 0; i <= M.rows; ++i) printf("p %d\n", M.rowPtr[i]);
   for (int p = 0; p < M.nnz; ++p) printf("v %d %.17g\n", M.colInd[p], M.values[p]);
+  // PCSR: c column stripes (nlibs/PCSR.cc:3-56), printed block by block
+  const int c = argc > 3 ? atoi(argv[3]) : 2;
+  PCSR P(M, c);
+  printf("pcsr %d %d\n", c, P.stride());
+  for (int b = 0; b < c; ++b) {
+    printf("blk %d %d\n", b, P.blocks[b].nnz);
+    for (int i = 0; i <= M.rows; ++i) printf("bp %d %d\n", b, P.blocks[b].rowPtr[i]);
+    for (int p = 0; p < P.blocks[b].nnz; ++p) printf("bv %d %d %.17g\n", b, P.blocks[b].colInd[p], P.blocks[b].values[p]);
+  }
+  P.dispose();
   Options o;
   const char* av[] = {"x", "-i", "some.snap", "--maxIters", "7", "-r", "SOMP", "--stride", "64", "-s"};
   process_args(10, (char**)av, o);

@@ -104,11 +104,13 @@ def test_cpp_ingest_matches_reference_golden(golden, tmp_path):
                            "-L" + os.path.join(ROOT, "sparse_matrix_with_flops_b200"), "-lb200spgemm",
                            "-Wl,-rpath," + os.path.join(ROOT, "sparse_matrix_with_flops_b200")])
 
-    def run(path, trans):
-        out = subprocess.run([exe, path, str(trans)], capture_output=True, text=True, timeout=60)
+    def run(path, trans, c=2):
+        out = subprocess.run([exe, path, str(trans), str(c)], capture_output=True, text=True, timeout=60)
         assert out.returncode == 0, out.stderr
         L = [ln.split() for ln in out.stdout.splitlines()]
-        return {"coo": [x for x in L if x[0] == "coo"][0], "removed": int([x for x in L if x[0] == "removed"][0][1]),
+        return {"pcsr": {"stride": int([x for x in L if x[0] == "pcsr"][0][2]),
+                         "bp": [(int(x[1]), int(x[2])) for x in L if x[0] == "bp"],
+                         "bv": [(int(x[1]), int(x[2]), float(x[3])) for x in L if x[0] == "bv"]},"coo": [x for x in L if x[0] == "coo"][0], "removed": int([x for x in L if x[0] == "removed"][0][1]),
                 "I": np.array([int(x[1]) for x in L if x[0] == "p"], dtype=np.int32),
                 "J": np.array([int(x[1]) for x in L if x[0] == "v"], dtype=np.int32),
                 "V": np.array([float(x[2]) for x in L if x[0] == "v"]),
@@ -126,3 +128,11 @@ def test_cpp_ingest_matches_reference_golden(golden, tmp_path):
     # rmclInit adds the missing self loops (vertices 1 and 2) and sets 1/rowcount
     assert list(sym["I"]) == [0, 3, 6, 8, 10] and np.allclose(sym["V"][:3], 1 / 3)
     assert t2["opts"][1:] == ["some.snap", "7", "4", "64", "1"]    # SOMP == 4 (nlibs/qrmcl.h:8)
+    # PCSR split of the rmclInit matrix against the checker's restatement of nlibs/PCSR.cc:3-56
+    for res, c in ((sym, 2), (run(os.path.join(ROOT, "tests", "golden", "sym4.mtx"), 1, 3), 3)):
+        Mx = ol.M(res["I"], res["J"], res["V"], len(res["I"]) - 1, len(res["I"]) - 1)
+        bp, rp, J, V = ol.o_pcsr_split(Mx, c)
+        assert res["pcsr"]["stride"] == (Mx.cols + c - 1) // c
+        got_rp = np.array([v for _, v in res["pcsr"]["bp"]], dtype=np.int32).reshape(c, Mx.rows + 1)
+        assert np.array_equal(got_rp, rp)
+        assert [x[1] for x in res["pcsr"]["bv"]] == list(J) and np.array_equal(np.array([x[2] for x in res["pcsr"]["bv"]]), V)
