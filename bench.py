@@ -422,39 +422,36 @@ def run_b200(args):
 
 
 def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
-    """The reference-facing call sequence with HOST buffers, every copy inside the timed region:
-    CSR::toGpuCSR (b200_csr_upload of the host matrix) -> gpuSpMMWrapper on row blocks
-    (b200_spgemm_device_rows) -> CSR::toCpuCSR of each block (b200_csr_download_rows: malloc'd
-    int CSR, freed by the caller) -> deviceDispose.  nnz(C) = 9.7e9 exceeds the reference's `int`
-    CSR, so the caller walks row blocks cut on the host so that each block's product count (an
-    upper bound of its nnz) fits an int."""
+    """The reference-facing call with HOST buffers, every copy inside the timed region:
+    b200_spgemm_csr_stream = flops_omp_CSR_SpMM's operands (host int CSR of A, twice) in, the
+    product out as malloc'd host int CSR row blocks handed to a callback that owns and frees
+    them.  nnz(C) = 9.7e9 exceeds the reference's `int` CSR, so the library cuts row blocks where
+    the intermediate-product prefix reaches 2e9 (an upper bound of a block's nnz)
+    and overlaps the download of block b with the computation of block b+1.  A rank passes its
+    own row range as IA + lo (offsets stay absolute, as in the reference's kernels)."""
     from sparse_matrix_with_flops_b200 import _lib
     ip, dp = _lib.c_int_p, _lib.c_double_p
-    prefix = host_flops_prefix(A)
-    mine = int(prefix[hi] - prefix[lo])
-    nblk = max(1, -(-mine // 2_000_000_000))
-    local_prefix = (prefix[lo:hi + 1] - prefix[lo]).astype(np.int64)
-    cuts = smf.arrayEqualPartition64(local_prefix, nblk) + lo
-    h2d = d2h = 0
+    h2d = d2h = nblk = 0
+    rp = A.rowPtr[lo:hi + 1]
+    same = lo == 0 and hi == A.rows
+
+    @_lib.block_fn
+    def sink(_user, r0, r1, IC, JC, Cv, nnzC):
+        nonlocal d2h, nblk
+        d2h += 4 * (r1 - r0 + 1) + 12 * nnzC
+        nblk += 1
+        for p in (IC, JC, Cv):                               # the caller owns the block
+            lib.b200_host_free(C.cast(p, C.c_void_p))
+        return 0
 
     def one():
-        nonlocal h2d, d2h
-        dA = A.toGpuCSR()                                   # H2D: rowPtr, colInd, values
-        h2d = 4 * (A.rows + 1) + 12 * A.nnz
-        d2h = 0
-        for b in range(nblk):
-            r0, r1 = int(cuts[b]), int(cuts[b + 1])
-            if r1 <= r0:
-                continue
-            dC = smf.gpuSpMMWrapper(dA, dA, r0, r1)
-            IC, JC, Cv, nnzC = ip(), ip(), dp(), C.c_int(0)
-            _lib.check(lib.b200_csr_download_rows(dC.handle, 0, r1 - r0, C.byref(IC), C.byref(JC),
-                                                  C.byref(Cv), C.byref(nnzC)))      # D2H
-            dC.deviceDispose()
-            d2h += 4 * (r1 - r0 + 1) + 12 * nnzC.value
-            for p in (IC, JC, Cv):
-                lib.b200_host_free(C.cast(p, C.c_void_p))
-        dA.deviceDispose()
+        nonlocal h2d, d2h, nblk
+        d2h = nblk = 0
+        h2d = 4 * (hi - lo + 1) + 12 * A.nnz + (0 if same else 4 * (A.rows + 1) + 12 * A.nnz)
+        _lib.check(lib.b200_spgemm_csr_stream(
+            rp.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
+            A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
+            hi - lo, A.cols, A.cols, 0, sink, None))
 
     one()  # warm-up (page-faults the pools, loads the kernels)
     barrier()
@@ -474,8 +471,8 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     return {"value": 2.0 * P / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
             "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
             "warmup": 1, "row_blocks": nblk,
-            "api": "b200_csr_upload + b200_spgemm_device_rows + b200_csr_download_rows (host malloc'd int CSR "
-                   "in/out), wall clock incl. H2D + D2H"}
+            "api": "b200_spgemm_csr_stream (host int CSR in, malloc'd host int CSR row blocks out through "
+                   "a callback), wall clock incl. H2D + D2H"}
 
 
 def main():

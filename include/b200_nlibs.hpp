@@ -113,6 +113,25 @@ struct CSR {
   CSR somp_spmm(const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
   CSR somp_spmm(thread_data_t*, const CSR& B, const int stride = 512) const { (void)stride; return mul(B, false, NULL); }
 
+  // The product as consecutive row blocks, for results beyond the int CSR (b200_spgemm_csr_stream):
+  // `sink(row_lo, row_hi, block)` gets each block (rowPtr[0] == 0) and owns it (block.dispose()).
+  template <class Sink>
+  void spmmBlocks(const CSR& B, Sink sink, long long blockProducts = 0) const {
+    assert(cols == B.rows);
+    b200_ensure_init();
+    struct Tramp {
+      Sink* sink; int cols;
+      static int call(void* u, int lo, int hi, int* IC, int* JC, QValue* Cv, int nnzC) {
+        Tramp* t = (Tramp*)u;
+        (*t->sink)(lo, hi, CSR(Cv, JC, IC, hi - lo, t->cols, nnzC));
+        return 0;
+      }
+    } tr = {&sink, B.cols};
+    b200_check(b200_spgemm_csr_stream(rowPtr, colInd, values, nnz, B.rowPtr, B.colInd, B.values, B.nnz,
+                                      rows, cols, B.cols, blockProducts, &Tramp::call, &tr),
+               "b200_spgemm_csr_stream");
+  }
+
   // ---- one rMCL iteration: this = Mgt, B = Mt (nlibs/CSR.cc:251-276) ---------------------
   CSR ompRmclOneStep(const CSR& B, thread_data_t*, const int stride) const { (void)stride; return mul(B, true, NULL); }
   CSR staticOmpRmclOneStep(const CSR& B, thread_data_t*, const int stride) const { (void)stride; return mul(B, true, NULL); }

@@ -37,7 +37,8 @@ enum {
   B200_ERR_INT32_OVERFLOW = 4, /* result does not fit the reference's int CSR (CSR.h:38) */
   B200_ERR_NO_DEVICE = 5,
   B200_ERR_NCCL = 6,
-  B200_ERR_NOT_INIT = 7
+  B200_ERR_NOT_INIT = 7,
+  B200_ERR_CALLBACK = 8 /* a b200_block_fn returned non-zero: the streamed product was abandoned */
 };
 
 /* Phase timings and counters of the last device call (all times in milliseconds, CUDA events
@@ -111,6 +112,25 @@ int b200_rmcl_iter(int maxIter, double eps,
                    int** IM, int** JM, double** M, int* nnzM,
                    int n, int* iters_done, double* chaos_hist);
 
+/* C = A x B delivered as consecutive row blocks, for products larger than the reference's
+ * `int` CSR can hold (nnz(A x A) of BASELINE.json's R-MAT scale 20 is 9.7e9).  Same operands
+ * as flops_omp_CSR_SpMM (nlibs/cpu_csr_kernel.h:95-98); the row space is cut where the
+ * intermediate-product prefix (dynamic_omp_CSR_flops, nlibs/flops_csr_kernel.cc:14-31) reaches
+ * `block_products` (<= 0: 2e9, so that every block's nnz fits an int; a single heavier row is a
+ * block of its own).  Each block is handed to `fn` as a malloc()'d int CSR with IC[0] = 0
+ * (IC has row_hi-row_lo+1 entries) — `fn` owns the three arrays (b200_host_free / free) and
+ * returns 0 to continue.  The download of block b runs on a copy stream and a helper thread
+ * while block b+1 is being computed, so a step costs about max(compute, PCIe) instead of their
+ * sum.  `fn` is called on the calling thread, in row order; it must not call back into the
+ * library (a transfer is in flight), except for b200_host_free, which also lets the library
+ * reuse the block's memory for a later block instead of faulting in fresh pages. */
+typedef int (*b200_block_fn)(void* user, int row_lo, int row_hi, int* IC, int* JC, double* C,
+                             int nnzC);
+int b200_spgemm_csr_stream(const int* IA, const int* JA, const double* A, int nnzA,
+                           const int* IB, const int* JB, const double* B, int nnzB,
+                           int m, int k, int n, long long block_products,
+                           b200_block_fn fn, void* user);
+
 /* ---- device-resident CSR (replaces CSR::toGpuCSR / toCpuCSR / deviceDispose,
  *      nlibs/CSR.cc:342-379) ------------------------------------------------------------ */
 
@@ -137,6 +157,10 @@ int b200_spgemm_device(b200_csr_t A, b200_csr_t B, b200_csr_t* C, b200_stats* st
 /* Rows [row_lo,row_hi) of A only: C has row_hi-row_lo rows. (Row-block / multi-GPU shard.) */
 int b200_spgemm_device_rows(b200_csr_t A, b200_csr_t B, int row_lo, int row_hi, b200_csr_t* C,
                             b200_stats* stats);
+/* b200_spgemm_csr_stream on uploaded operands (gpuSpMMWrapper + CSR::toCpuCSR per row block,
+ * nlibs/gpus/gpu_csr_kernel.cu:128-172, nlibs/CSR.cc:356-371, pipelined). */
+int b200_spgemm_device_stream(b200_csr_t A, b200_csr_t B, long long block_products,
+                              b200_block_fn fn, void* user);
 /* One rMCL iteration on the device.  Replaces gpuRmclOneStepWrapper
  * (nlibs/gpus/gpu_csr_kernel.cu:243-279). */
 int b200_rmcl_step_device(b200_csr_t Mgt, b200_csr_t Mt, b200_csr_t* newMt, double* chaos,

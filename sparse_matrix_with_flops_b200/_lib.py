@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libb200spgemm.so")
 c_int_p = C.POINTER(C.c_int)
 c_double_p = C.POINTER(C.c_double)
 c_ll_p = C.POINTER(C.c_longlong)
+# b200_block_fn: int fn(void* user, int row_lo, int row_hi, int* IC, int* JC, double* C, int nnzC)
+block_fn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, C.c_int)
 csr_t = C.c_void_p
 
 
@@ -66,6 +68,9 @@ SIGNATURES = {
     "b200_rmcl_iter": (C.c_int, [C.c_int, C.c_double, c_int_p, c_int_p, c_double_p, C.c_int, c_int_p,
                                  c_int_p, c_double_p, C.c_int, C.POINTER(c_int_p), C.POINTER(c_int_p),
                                  C.POINTER(c_double_p), c_int_p, C.c_int, c_int_p, c_double_p]),
+    "b200_spgemm_csr_stream": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, c_int_p, c_int_p,
+                                         c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                         block_fn, C.c_void_p]),
     "b200_csr_upload": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(csr_t)]),
     "b200_csr_info": (C.c_int, [csr_t, c_int_p, c_int_p, c_ll_p]),
@@ -80,6 +85,7 @@ SIGNATURES = {
     "b200_spgemm_device": (C.c_int, [csr_t, csr_t, C.POINTER(csr_t), C.POINTER(Stats)]),
     "b200_spgemm_device_rows": (C.c_int, [csr_t, csr_t, C.c_int, C.c_int, C.POINTER(csr_t),
                                           C.POINTER(Stats)]),
+    "b200_spgemm_device_stream": (C.c_int, [csr_t, csr_t, C.c_longlong, block_fn, C.c_void_p]),
     "b200_rmcl_step_device": (C.c_int, [csr_t, csr_t, C.POINTER(csr_t), c_double_p, C.POINTER(Stats)]),
     "b200_rmcl_step_device_rows": (C.c_int, [csr_t, csr_t, C.c_int, C.c_int, C.POINTER(csr_t),
                                              c_double_p, C.POINTER(Stats)]),

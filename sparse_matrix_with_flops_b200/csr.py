@@ -90,6 +90,33 @@ class CSR:
             out.chaos = chaos.value
         return out
 
+    def spmm_blocks(self, B, on_block, block_products=0):
+        """C = self x B as consecutive row blocks (b200_spgemm_csr_stream): for products whose nnz
+        exceeds the reference's int CSR.  `on_block(row_lo, row_hi, CSR_block)` is called in row
+        order; a block's rowPtr starts at 0.  A truthy return value stops the product
+        (B200Error with code 8)."""
+        assert self.cols == B.rows
+        _ensure_init()
+        lib = _lib.load()
+        failure = []
+
+        def tramp(_user, lo, hi, IC, JC, Cv, nnz):
+            try:
+                blk = CSR(_take(Cv, nnz, np.float64), _take(JC, nnz, np.int32),
+                          _take(IC, hi - lo + 1, np.int32), hi - lo, B.cols, nnz)
+                return 1 if on_block(lo, hi, blk) else 0
+            except BaseException as e:      # never unwind through the C frames
+                failure.append(e)
+                return 1
+
+        cb = _lib.block_fn(tramp)
+        rc = lib.b200_spgemm_csr_stream(_ip(self.rowPtr), _ip(self.colInd), _dp(self.values), self.nnz,
+                                        _ip(B.rowPtr), _ip(B.colInd), _dp(B.values), B.nnz,
+                                        self.rows, self.cols, B.cols, int(block_products), cb, None)
+        if failure:
+            raise failure[0]
+        check(rc)
+
     def flops_spmm(self, B, stride=512):
         """CSR::flops_spmm (nlibs/CSR.cc:182-194) — `stride` is accepted and unused."""
         return self._mul(B)

@@ -2,12 +2,21 @@
 // device-handle entry points.  No algorithm lives here; see spgemm.cu.
 #include <limits.h>
 #include <stdint.h>
+#include <malloc.h>
 #include <sys/mman.h>
+#include <unistd.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -65,7 +74,11 @@ __global__ void k_row_argmax(const int64_t* __restrict__ rp, const int* __restri
 // thread plus first-touch page faults).  Instead: DMA through two pinned buffers on a second
 // stream while all host cores copy the previous chunk between the pinned buffer and the user's
 // block (which also first-touches a fresh malloc block in parallel).
-constexpr size_t PIN_BYTES = 128u << 20;
+// Chunks of 32 MB: large enough for the full DMA rate, small enough that the library's own small
+// read-backs (row totals, bin counts: the same copy engine serves them) wait at most ~1 ms behind
+// a streamed download; with 128 MB chunks a row block computed next to a download took 200 ms
+// instead of 30.
+constexpr size_t PIN_BYTES = 32u << 20;
 
 int ensure_staging() {
   Ctx& c = ctx();
@@ -89,31 +102,62 @@ void advise_huge(void* p, size_t bytes) {
   if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 }
 
-// one contiguous piece per host thread (large pieces let memcpy use non-temporal stores, which
-// spare the destination the read-for-ownership of a regular store)
-void parallel_copy(void* dst, const void* src, size_t bytes) {
-#pragma omp parallel
+// Streaming copy: non-temporal 16-byte stores spare the destination the read-for-ownership of a
+// regular store and keep 128 MB chunks out of the host caches.  Measured on the B200 box (16
+// cores, tools/micro/d2h_rate.cu): pinned -> fresh malloc block 35 GB/s against 15 GB/s for
+// memcpy, pinned -> touched block 57 against 36; the DMA itself runs at 56.6 GB/s.
+void stream_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__SSE2__)
+  const size_t head = std::min(bytes, (size_t)((16 - ((uintptr_t)dst & 15)) & 15));
+  if (head) { memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+  const size_t n16 = bytes / 16;
+  __m128i* d = (__m128i*)dst;
+  const __m128i* s = (const __m128i*)src;
+  size_t i = 0;
+  for (; i + 4 <= n16; i += 4) {
+    const __m128i a = _mm_loadu_si128(s + i), b = _mm_loadu_si128(s + i + 1);
+    const __m128i c = _mm_loadu_si128(s + i + 2), e = _mm_loadu_si128(s + i + 3);
+    _mm_stream_si128(d + i, a); _mm_stream_si128(d + i + 1, b);
+    _mm_stream_si128(d + i + 2, c); _mm_stream_si128(d + i + 3, e);
+  }
+  for (; i < n16; ++i) _mm_stream_si128(d + i, _mm_loadu_si128(s + i));
+  if (bytes & 15) memcpy(dst + n16 * 16, src + n16 * 16, bytes & 15);
+  _mm_sfence();
+#else
+  memcpy(dst, src, bytes);
+#endif
+}
+
+// one contiguous piece per host thread; `spare` cores are left to other busy threads (the
+// caller of the streamed product spins in the CUDA runtime while the download worker copies)
+void parallel_copy(void* dst, const void* src, size_t bytes, int spare = 0) {
+#pragma omp parallel num_threads(std::max(1, omp_get_max_threads() - spare))
   {
     const size_t nt = (size_t)omp_get_num_threads(), t = (size_t)omp_get_thread_num();
     const size_t piece = (((bytes + nt - 1) / nt) + 4095) & ~(size_t)4095;
     const size_t off = t * piece;
-    if (off < bytes) memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
+    if (off < bytes) stream_copy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
   }
 }
 
-// device -> host block; everything queued on the library stream before the call is waited for
-int d2h_staged(void* dst, const void* src, size_t bytes) {
+// device -> host block.  ordered == true: everything queued on the library stream before the
+// call is waited for.  ordered == false (download worker): only the copy stream is touched; the
+// submitting thread has already made the copy stream wait for the producer.
+int d2h_staged(void* dst, const void* src, size_t bytes, bool ordered = true) {
   Ctx& c = ctx();
   if (!bytes) return B200_OK;
   if (bytes < (4u << 20)) {
-    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
-    B200_CUDA(cudaStreamSynchronize(c.stream));
+    cudaStream_t st = ordered ? c.stream : c.copy_stream;
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
   }
-  int rc = ensure_staging();
-  if (rc) return rc;
-  B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));
-  B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+  if (ordered) {
+    int rc = ensure_staging();
+    if (rc) return rc;
+    B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));
+    B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+  }
   const size_t nchunks = (bytes + PIN_BYTES - 1) / PIN_BYTES;
   for (size_t k = 0; k <= nchunks; ++k) {
     if (k < nchunks) {
@@ -124,7 +168,7 @@ int d2h_staged(void* dst, const void* src, size_t bytes) {
     if (k > 0) {
       const size_t off = (k - 1) * PIN_BYTES, len = std::min(PIN_BYTES, bytes - off);
       B200_CUDA(cudaEventSynchronize(c.pin_ev[(k - 1) & 1]));
-      parallel_copy((char*)dst + off, c.pin[(k - 1) & 1], len);
+      parallel_copy((char*)dst + off, c.pin[(k - 1) & 1], len, ordered ? 0 : 1);
     }
   }
   return B200_OK;
@@ -155,7 +199,96 @@ int h2d_staged(void* dst, const void* src, size_t bytes) {
   return B200_OK;
 }
 
-int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V, int* nnz) {
+// ---- host block cache ---------------------------------------------------------------------------
+// Result blocks are plain malloc() memory that the caller owns and may free().  A 10 GB block
+// that comes fresh from the OS costs ~0.3 s of page faults on the B200 box before the first
+// byte lands (tools/micro/d2h_rate.cu: 35 GB/s into fresh pages, 57 GB/s into touched ones, the
+// DMA runs at 56.6).  A caller that hands blocks back through b200_host_free() instead of
+// free() lets the library keep them (still malloc blocks, their capacity read back with
+// malloc_usable_size) for the next download, up to B200_HOST_CACHE_GB (default: a quarter of the
+// physical memory, at most 64 GB; 0 turns the cache off).
+struct HostCache {
+  std::mutex mu;
+  std::vector<std::pair<size_t, void*>> blocks;   // (capacity, pointer)
+  size_t total = 0, limit = 0;
+  long hits = 0, misses = 0;
+  bool limit_known = false;
+  static constexpr size_t BIG = (size_t)64 << 20;
+
+  size_t cap_limit() {
+    if (!limit_known) {
+      limit_known = true;
+      const char* e = getenv("B200_HOST_CACHE_GB");
+      if (e) {
+        limit = (size_t)(atof(e) * (double)((size_t)1 << 30));
+      } else {
+        const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+        const size_t phys = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz : 0;
+        limit = std::min(phys / 4, (size_t)64 << 30);
+      }
+    }
+    return limit;
+  }
+  // smallest kept block that holds `bytes` without wasting more than 3/4 of itself
+  void* take(size_t bytes) {
+    if (bytes < BIG) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    int best = -1;
+    for (int i = 0; i < (int)blocks.size(); ++i)
+      if (blocks[i].first >= bytes && blocks[i].first / 4 <= bytes &&
+          (best < 0 || blocks[i].first < blocks[best].first)) best = i;
+    if (best < 0) { ++misses; return nullptr; }
+    ++hits;
+    void* p = blocks[best].second;
+    total -= blocks[best].first;
+    blocks.erase(blocks.begin() + best);
+    return p;
+  }
+  // true: kept; false: the caller frees it
+  bool give(void* p) {
+    const size_t cap = malloc_usable_size(p);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cap < BIG || cap > cap_limit()) return false;
+    while (total + cap > limit && !blocks.empty()) {     // make room: smallest blocks go first
+      int s = 0;
+      for (int i = 1; i < (int)blocks.size(); ++i) if (blocks[i].first < blocks[s].first) s = i;
+      if (blocks[s].first >= cap) return false;            // everything kept is at least as useful
+      total -= blocks[s].first;
+      free(blocks[s].second);
+      blocks.erase(blocks.begin() + s);
+    }
+    if (total + cap > limit) return false;
+    blocks.push_back(std::make_pair(cap, p));
+    total += cap;
+    return true;
+  }
+  void drop_all() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& b : blocks) free(b.second);
+    blocks.clear();
+    total = 0;
+  }
+};
+HostCache& host_cache() { static HostCache* h = new HostCache; return *h; }
+
+void* host_block_alloc(size_t bytes) {
+  void* p = host_cache().take(bytes);
+  if (p) return p;
+  p = malloc(bytes);
+  advise_huge(p, bytes);
+  return p;
+}
+
+// A row block on its way to the host: the three malloc()'d arrays plus the device range that
+// still has to be copied into JC / C.
+struct HostBlock {
+  int* I = nullptr; int* J = nullptr; double* V = nullptr;
+  int64_t begin = 0, cnt = 0;
+  void drop() { free(I); free(J); free(V); I = nullptr; J = nullptr; V = nullptr; }
+};
+
+// allocate the host block and bring the (rebased, 32-bit) row offsets over; library stream
+int download_prepare(const DevCSR& d, int lo, int hi, HostBlock* hb) {
   Ctx& c = ctx();
   if (lo < 0 || hi > d.rows || lo > hi) { set_error("row range out of bounds"); return B200_ERR_BAD_ARG; }
   const int m = hi - lo;
@@ -168,26 +301,104 @@ int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V,
     set_error("row block holds more than INT_MAX entries; download a smaller block");
     return B200_ERR_INT32_OVERFLOW;
   }
-  int* hi32 = (int*)malloc(((size_t)m + 1) * sizeof(int));
-  int* hj = (int*)malloc(((size_t)cnt + 1) * sizeof(int));
-  double* hv = (double*)malloc(((size_t)cnt + 1) * sizeof(double));
-  if (!hi32 || !hj || !hv) { free(hi32); free(hj); free(hv); set_error("host malloc failed"); return B200_ERR_HOST_ALLOC; }
-  advise_huge(hj, (size_t)cnt * sizeof(int));
-  advise_huge(hv, (size_t)cnt * sizeof(double));
+  hb->begin = ends[0]; hb->cnt = cnt;
+  hb->I = (int*)malloc(((size_t)m + 1) * sizeof(int));
+  hb->J = (int*)host_block_alloc(((size_t)cnt + 1) * sizeof(int));
+  hb->V = (double*)host_block_alloc(((size_t)cnt + 1) * sizeof(double));
+  if (!hb->I || !hb->J || !hb->V) { hb->drop(); set_error("host malloc failed"); return B200_ERR_HOST_ALLOC; }
   int* d32 = nullptr;
-  B200_CUDA(dalloc(&d32, (size_t)m + 1));
+  cudaError_t e = dalloc(&d32, (size_t)m + 1);
+  if (e != cudaSuccess) { hb->drop(); B200_CUDA(e); }
   k_i64_to_i32_rebased<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c.stream>>>(d.rowptr + lo, d32, m + 1);
-  B200_CUDA(cudaMemcpyAsync(hi32, d32, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  e = cudaMemcpyAsync(hb->I, d32, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
   dfree(d32);
-  B200_CUDA(cudaStreamSynchronize(c.stream));
-  if (cnt) {
-    int rc = d2h_staged(hj, d.col + ends[0], (size_t)cnt * sizeof(int));
-    if (!rc) rc = d2h_staged(hv, d.val + ends[0], (size_t)cnt * sizeof(double));
-    if (rc) { free(hi32); free(hj); free(hv); return rc; }
-  }
-  *I = hi32; *J = hj; *V = hv; *nnz = (int)cnt;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+  if (e != cudaSuccess) { hb->drop(); B200_CUDA(e); }
   return B200_OK;
 }
+
+// the bulk of the block: columns and values through the pinned pipeline
+int download_bulk(const DevCSR& d, const HostBlock& hb, bool ordered) {
+  if (!hb.cnt) return B200_OK;
+  int rc = d2h_staged(hb.J, d.col + hb.begin, (size_t)hb.cnt * sizeof(int), ordered);
+  if (!rc) rc = d2h_staged(hb.V, d.val + hb.begin, (size_t)hb.cnt * sizeof(double), ordered);
+  return rc;
+}
+
+int download_rows(const DevCSR& d, int lo, int hi, int** I, int** J, double** V, int* nnz) {
+  HostBlock hb;
+  int rc = download_prepare(d, lo, hi, &hb);
+  if (rc) return rc;
+  rc = download_bulk(d, hb, true);
+  if (rc) { hb.drop(); return rc; }
+  *I = hb.I; *J = hb.J; *V = hb.V; *nnz = (int)hb.cnt;
+  return B200_OK;
+}
+
+// ---- download worker ----------------------------------------------------------------------------
+// One helper thread that runs download_bulk for the streamed product while the calling thread
+// computes the next row block.  It touches the copy stream, the pinned buffers and their events
+// only; the library stream, the device pool and the error string stay with the calling thread.
+// The thread is detached and the object is never destroyed: a joinable thread (or a condition
+// variable with a waiter) inside a static object blocks the process at exit.
+struct Downloader {
+  std::mutex mu;
+  std::condition_variable cv;
+  bool started = false, has_job = false, busy = false, quit = false, exited = false;
+  DevCSR src;
+  HostBlock hb;
+  int rc = B200_OK;
+  std::string err;
+
+  void loop(int device) {
+    cudaSetDevice(device);
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return has_job || quit; });
+      if (quit) break;
+      has_job = false;
+      lk.unlock();
+      const int r = download_bulk(src, hb, false);
+      const std::string e = r ? std::string(b200_last_error()) : std::string();
+      lk.lock();
+      rc = r; err = e; busy = false;
+      cv.notify_all();
+    }
+    exited = true;
+    cv.notify_all();
+  }
+  // calling thread: the block's producer has finished on the library stream (run_pipeline ends
+  // with a synchronisation); make the copy stream wait for it anyway, then hand the job over
+  int submit(const DevCSR& d, const HostBlock& block) {
+    Ctx& c = ctx();
+    int r = ensure_staging();
+    if (r) return r;
+    B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));
+    B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!started) { std::thread(&Downloader::loop, this, c.device).detach(); started = true; }
+    src = d; hb = block; has_job = true; busy = true;
+    cv.notify_all();
+    return B200_OK;
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !busy; });
+    if (rc) set_error(err);
+    return rc;
+  }
+  // b200_finalize: the worker leaves before the copy stream and the pinned buffers go away
+  void stop() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (!started) return;
+    cv.wait(lk, [&] { return !busy; });
+    quit = true;
+    cv.notify_all();
+    cv.wait(lk, [&] { return exited; });
+    started = quit = exited = has_job = false;
+  }
+};
+Downloader& downloader() { static Downloader* d = new Downloader; return *d; }
 
 int upload(const int* I, const int* J, const double* V, int rows, int cols, int nnz, DevCSR* out) {
   Ctx& c = ctx();
@@ -233,6 +444,10 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 
+void b200_host_free(void* p) {
+  if (p && !host_cache().give(p)) free(p);
+}
+
 int b200_init(int device) {
   Ctx& c = ctx();
   if (c.ready) {
@@ -271,6 +486,8 @@ int b200_init(int device) {
 int b200_finalize(void) {
   Ctx& c = ctx();
   if (!c.ready) return B200_OK;
+  downloader().stop();
+  host_cache().drop_all();
   cudaStreamSynchronize(c.stream);
   for (auto& ev : c.ev) { cudaEventDestroy(ev); ev = nullptr; }
   for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
@@ -392,6 +609,102 @@ int b200_spgemm_device_rows(b200_csr_t A, b200_csr_t B, int row_lo, int row_hi, 
 int b200_spgemm_device(b200_csr_t A, b200_csr_t B, b200_csr_t* C, b200_stats* stats) {
   if (!A) { set_error("null handle"); return B200_ERR_BAD_ARG; }
   return b200_spgemm_device_rows(A, B, 0, A->d.rows, C, stats);
+}
+
+// Row blocks of A x B, block b on its way over PCIe while block b+1 is computed.
+static int stream_blocks(const DevCSR& A, const DevCSR& B, long long block_products,
+                         b200_block_fn fn, void* user) {
+  Ctx& c = ctx();
+  const int m = A.rows;
+  if (block_products <= 0) block_products = 2000000000LL;
+  std::vector<long long> prefix((size_t)m + 1, 0);
+  {
+    int64_t* d_prefix = nullptr;
+    B200_CUDA(dalloc(&d_prefix, (size_t)m + 1));
+    int rc = flops_prefix_device(A, B, 0, m, d_prefix);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(prefix.data(), d_prefix, ((size_t)m + 1) * sizeof(long long),
+                                 cudaMemcpyDeviceToHost, c.stream);
+    dfree(d_prefix);
+    if (rc) return rc;
+    B200_CUDA(e);
+    B200_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  Downloader& dl = downloader();
+  const bool prof = getenv("B200_PROF") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  struct Flight { bool on = false; DevCSR dev; HostBlock hb; int lo = 0, hi = 0; } fly, done;
+  // wait for the block in flight and free its device copy; it becomes `done`
+  auto land = [&]() -> int {
+    if (!fly.on) return B200_OK;
+    const int rc = dl.wait();
+    release(fly.dev);
+    if (rc) { fly.hb.drop(); fly.on = false; return rc; }
+    done = fly; fly.on = false;
+    return B200_OK;
+  };
+  // pass the landed block on; the callback owns the arrays from here
+  auto deliver = [&]() -> int {
+    if (!done.on) return B200_OK;
+    done.on = false;
+    if (fn(user, done.lo, done.hi, done.hb.I, done.hb.J, done.hb.V, (int)done.hb.cnt)) {
+      set_error("block callback asked to stop");
+      return B200_ERR_CALLBACK;
+    }
+    return B200_OK;
+  };
+  int lo = 0;
+  do {
+    // largest hi with prefix[hi] - prefix[lo] <= block_products, at least one row
+    int hi = (int)(std::upper_bound(prefix.begin() + lo, prefix.end(), prefix[lo] + block_products) -
+                   prefix.begin()) - 1;
+    hi = std::min(m, std::max(hi, lo + 1));
+    DevCSR dC;
+    HostBlock hb;
+    const double t0 = now();
+    b200_stats st;
+    memset(&st, 0, sizeof st);
+    int rc = run_pipeline(A, B, lo, hi, MODE_SPGEMM, &dC, nullptr, prof ? &st : nullptr);
+    const double t1 = now();
+    if (!rc) rc = download_prepare(dC, 0, hi - lo, &hb);
+    const double t2 = now();
+    // block b-1 has had the whole computation of block b to arrive; start block b's transfer
+    // before the callback sees block b-1, so that the copy engine never waits for the callback
+    const int rc_land = land();
+    const double t3 = now();
+    if (!rc) rc = rc_land;
+    if (!rc) rc = dl.submit(dC, hb);
+    if (rc) {
+      release(dC); hb.drop();
+      if (done.on) { done.hb.drop(); done.on = false; }
+      return rc;
+    }
+    fly.on = true; fly.dev = dC; fly.hb = hb; fly.lo = lo; fly.hi = hi;
+    rc = deliver();
+    if (prof) {
+      double kern = 0.0;
+      for (int b = 0; b < 16; ++b) kern += st.ms_sym_bin[b] + st.ms_num_bin[b];
+      fprintf(stderr, "[b200 stream] on-stream %.1f ms (flops %.1f symbolic %.1f numeric %.1f other %.1f; kernels alone %.1f)\n",
+              st.ms_total, st.ms_flops, st.ms_symbolic, st.ms_numeric, st.ms_other, kern);
+    }
+    if (prof)
+      fprintf(stderr, "[b200 stream] rows %d-%d nnz %lld: compute %.1f prepare %.1f wait-for-previous %.1f callback %.1f ms; host cache %ld hits %ld misses\n",
+              lo, hi, (long long)hb.cnt, t1 - t0, t2 - t1, t3 - t2, now() - t3, host_cache().hits, host_cache().misses);
+    if (rc) { land(); if (done.on) { done.hb.drop(); done.on = false; } return rc; }
+    lo = hi;
+  } while (lo < m);
+  int rc = land();
+  if (!rc) rc = deliver();
+  return rc;
+}
+
+int b200_spgemm_device_stream(b200_csr_t A, b200_csr_t B, long long block_products,
+                              b200_block_fn fn, void* user) {
+  B200_REQUIRE_INIT();
+  int rc = check_mul(A, B, 0, A ? A->d.rows : 0);
+  if (rc) return rc;
+  if (!fn) { set_error("null block callback"); return B200_ERR_BAD_ARG; }
+  return stream_blocks(A->d, B->d, block_products, fn, user);
 }
 
 int b200_rmcl_step_device_rows(b200_csr_t Mgt, b200_csr_t Mt, int row_lo, int row_hi,
@@ -529,6 +842,27 @@ int b200_spgemm_csr(const int* IA, const int* JA, const double* A, int nnzA, con
                     const int* JB, const double* B, int nnzB, int** IC, int** JC, double** C,
                     int* nnzC, int m, int k, int n) {
   return host_mul(MODE_SPGEMM, IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, nullptr);
+}
+
+int b200_spgemm_csr_stream(const int* IA, const int* JA, const double* A, int nnzA, const int* IB,
+                           const int* JB, const double* B, int nnzB, int m, int k, int n,
+                           long long block_products, b200_block_fn fn, void* user) {
+  B200_REQUIRE_INIT();
+  if (!fn) { set_error("null block callback"); return B200_ERR_BAD_ARG; }
+  DevCSR dA, dB;
+  int rc = upload(IA, JA, A, m, k, nnzA, &dA);
+  if (rc) return rc;
+  // A x A with the very same arrays (the headline case): one device copy serves both sides
+  const bool same = IB == IA && JB == JA && B == A && nnzB == nnzA && k == m && n == k;
+  if (!same) {
+    rc = upload(IB, JB, B, k, n, nnzB, &dB);
+    if (rc) { release(dA); return rc; }
+  }
+  rc = stream_blocks(dA, same ? dA : dB, block_products, fn, user);
+  release(dA);
+  if (!same) release(dB);
+  cudaStreamSynchronize(ctx().stream);
+  return rc;
 }
 
 int b200_rmcl_onestep_csr(const int* IA, const int* JA, const double* A, int nnzA, const int* IB,

@@ -203,6 +203,6 @@ int b200_synth_planted(int n, int nblocks, int intra, int inter, unsigned long l
   return edges_to_csr(n, r, c, true, IA, JA, A, nnz);
 }
 
-void b200_host_free(void* p) { free(p); }
+// b200_host_free lives in capi.cu (it feeds the host block cache)
 
 }  // extern "C"

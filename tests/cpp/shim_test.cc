@@ -55,6 +55,26 @@ int main() {
   CSR C4 = dC.toCpuCSR();
   diffs += report("gpuSpMMWrapper vs flops_spmm", C4.isEqual(C1, 0.0));
   dC.deviceDispose(); dA.deviceDispose();
+  // the streamed row-block product, cut every 60 intermediate products, glued back together
+  {
+    struct Glue {
+      std::vector<int> I, J; std::vector<double> V; int next;
+      void operator()(int lo, int hi, CSR blk) {
+        if (lo != next) I.assign(1, -1);               // blocks must arrive in row order
+        next = hi;
+        for (int i = 0; i < hi - lo; ++i) I.push_back((int)J.size() + blk.rowPtr[i + 1]);
+        J.insert(J.end(), blk.colInd, blk.colInd + blk.nnz);
+        V.insert(V.end(), blk.values, blk.values + blk.nnz);
+        blk.dispose();
+      }
+    } g;
+    g.I.assign(1, 0); g.next = 0;
+    struct Ref { Glue* g; void operator()(int lo, int hi, CSR blk) { (*g)(lo, hi, blk); } } ref = {&g};
+    A.spmmBlocks(A, ref, 60);
+    bool ok = g.next == n && (int)g.I.size() == n + 1 && (int)g.J.size() == C1.nnz;
+    if (ok) ok = CSR(g.V.data(), g.J.data(), g.I.data(), n, n, (int)g.J.size()).isEqual(C1, 0.0);
+    diffs += report("spmmBlocks vs flops_spmm", ok);
+  }
   // PCSR: column-striped product equals the plain one (correctTests/pcsrTest.cc)
   PCSR P(A, 3);
   CSR C5 = P.leftMultiply(A);

@@ -35,6 +35,8 @@ def test_no_cpu_fallback(smf):
     A = smf.synth_rmat(5, 4, 1, True)
     with pytest.raises(smf._lib.B200Error):
         A.flops_spmm(A)
+    with pytest.raises(smf._lib.B200Error):
+        A.spmm_blocks(A, lambda lo, hi, blk: 0)
 
 
 def test_product_does_not_touch_the_oracle():
