@@ -493,6 +493,8 @@ int b200_finalize(void) {
   for (auto& ev : c.kev) { cudaEventDestroy(ev); ev = nullptr; }
   if (c.bm_store) { cudaFree(c.bm_store); c.bm_store = nullptr; c.bm_store_words = 0; }
   c.bm_store_capped = false;
+  if (c.rb_host) { cudaFreeHost(c.rb_host); c.rb_host = nullptr; c.rb_dev = nullptr; }
+  rb_reset();
   if (c.arena_col) { cudaFree(c.arena_col); cudaFree(c.arena_val); c.arena_col = nullptr; c.arena_val = nullptr; c.arena_cap = 0; }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;

@@ -59,8 +59,24 @@ struct Ctx {
   int* arena_col = nullptr;
   double* arena_val = nullptr;
   size_t arena_cap = 0;
+  // small read-backs (row totals, bin counts): a kernel writes them into mapped pinned memory
+  // instead of a cudaMemcpy, because the device-to-host copy engine may be busy for 100+ ms with
+  // a streamed download (profiles/r1_stream_blocks_rmat20.txt)
+  static constexpr int RB_BYTES = 8192, RB_MAX = 16;
+  unsigned char* rb_host = nullptr;
+  unsigned char* rb_dev = nullptr;
+  size_t rb_used = 0;
+  int rb_n = 0;
+  struct { void* dst; size_t off, bytes; } rb_pending[RB_MAX];
 };
 Ctx& ctx();
+
+// Queue a small device -> host read-back on `st`; the value is in *dst after sync_fetch(st).
+// dst must stay valid until then; rb_reset() forgets queued read-backs (entry points call it, so
+// that an error return between the two cannot leave a pointer to a dead stack frame behind).
+cudaError_t d2h_small(void* dst, const void* src, size_t bytes, cudaStream_t st);
+cudaError_t sync_fetch(cudaStream_t st);
+void rb_reset();
 
 void set_error(const std::string& s);
 int fail_cuda(cudaError_t e, const char* what, const char* file, int line);

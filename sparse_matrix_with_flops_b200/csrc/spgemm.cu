@@ -1721,8 +1721,8 @@ int make_bins(const unsigned char* d_bin, int m, Bins* out, int* launches) {
     k_bin_hist<<<grid, 256, 0, c.stream>>>(d_bin, m, d_hist);
     ++*launches;
   }
-  B200_CUDA(cudaMemcpyAsync(out->cnt, d_hist, 16 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  B200_CUDA(cudaStreamSynchronize(c.stream));
+  B200_CUDA(d2h_small(out->cnt, d_hist, 16 * sizeof(int), c.stream));
+  B200_CUDA(sync_fetch(c.stream));
   out->off[0] = 0;
   for (int b = 0; b < 16; ++b) out->off[b + 1] = out->off[b] + out->cnt[b];
   B200_CUDA(cudaMemcpyAsync(d_hist + 16, out->off, 16 * sizeof(int), cudaMemcpyHostToDevice, c.stream));
@@ -1743,6 +1743,53 @@ int set_smem(K kernel, size_t bytes) {
 constexpr int BT_BIG = 1024;
 
 }  // namespace
+
+// ---- small read-backs through mapped pinned memory (common.cuh) -------------------------------
+__global__ void k_readback(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int bytes) {
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+void rb_reset() {
+  Ctx& c = ctx();
+  c.rb_n = 0;
+  c.rb_used = 0;
+}
+
+cudaError_t d2h_small(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  Ctx& c = ctx();
+  if (!c.rb_host) {
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, Ctx::RB_BYTES, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+      c.rb_host = (unsigned char*)h;
+      c.rb_dev = (unsigned char*)d;
+    } else {
+      cudaGetLastError();
+      if (h) cudaFreeHost(h);
+    }
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (!c.rb_host || c.rb_n == Ctx::RB_MAX || c.rb_used + need > (size_t)Ctx::RB_BYTES)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);   // still correct, may wait
+  k_readback<<<1, 128, 0, st>>>((const unsigned char*)src, c.rb_dev + c.rb_used, (int)bytes);
+  c.rb_pending[c.rb_n].dst = dst;
+  c.rb_pending[c.rb_n].off = c.rb_used;
+  c.rb_pending[c.rb_n].bytes = bytes;
+  ++c.rb_n;
+  c.rb_used += need;
+  return cudaGetLastError();
+}
+
+cudaError_t sync_fetch(cudaStream_t st) {
+  Ctx& c = ctx();
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess)
+    for (int i = 0; i < c.rb_n; ++i) memcpy(c.rb_pending[i].dst, c.rb_host + c.rb_pending[i].off, c.rb_pending[i].bytes);
+  c.rb_n = 0;
+  c.rb_used = 0;
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------
 // CSR::makeOrdered on the device (nlibs/CSR.cc:73-86): sort every row by column.  Runs once
@@ -1769,7 +1816,7 @@ int sort_rows_device(DevCSR* d) {
   d->col = col2;
   d->val = val2;
   d->sorted_rows = true;
-  B200_CUDA(cudaStreamSynchronize(c.stream));
+  B200_CUDA(sync_fetch(c.stream));
   return B200_OK;
 }
 
@@ -1796,13 +1843,14 @@ int check_sorted_device(DevCSR* d) {
   if (d->rows == 0 || d->nnz == 0) return B200_OK;
   int* d_flag = nullptr;
   int h = 1;
+  rb_reset();
   B200_CUDA(dalloc(&d_flag, 1));
   B200_CUDA(cudaMemcpyAsync(d_flag, &h, sizeof(int), cudaMemcpyHostToDevice, c.stream));
   const long long threads = (long long)d->rows * 32;
   k_check_sorted<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d->rowptr, d->col, d->rows, d_flag);
-  B200_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  B200_CUDA(d2h_small(&h, d_flag, sizeof(int), c.stream));
   dfree(d_flag);
-  B200_CUDA(cudaStreamSynchronize(c.stream));
+  B200_CUDA(sync_fetch(c.stream));
   d->sorted_rows = h != 0;
   return B200_OK;
 }
@@ -1857,6 +1905,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const int m = row_hi - row_lo;
   const int n = B.cols;
   int launches = 0;
+  rb_reset();
   if (stats) memset(stats, 0, sizeof(*stats));
   *C = DevCSR();
   // on any early return the result is left empty (callers release it) and every temporary is
@@ -2061,7 +2110,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       // grow only for a real gain: the budget moves a little from call to call with what else
       // is allocated, and re-allocating tens of GB costs ~15 ms
       if (new_words > c.bm_store_words + c.bm_store_words / 4) {
-        B200_CUDA(cudaStreamSynchronize(st));
+        B200_CUDA(sync_fetch(st));
         if (c.bm_store) cudaFree(c.bm_store);
         c.bm_store = nullptr;
         c.bm_store_words = 0;
@@ -2143,8 +2192,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ++launches;
   }
   long long h_tot[2] = {0, 0};  // unpruned nnz, products
-  B200_CUDA(cudaMemcpyAsync(&h_tot[0], d_urp + m, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaMemcpyAsync(&h_tot[1], d_P, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(d2h_small(&h_tot[0], d_urp + m, sizeof(long long), st));
+  B200_CUDA(d2h_small(&h_tot[1], d_P, sizeof(long long), st));
   Bins nb;
   rc = make_bins(d_nbin, m, &nb, &launches);  // synchronises the stream
   T.adopt(nb.d_list);
@@ -2172,7 +2221,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     B200_CUDA(T.alloc(&C->val, (size_t)unpruned));
   } else {
     if (c.arena_cap < (size_t)unpruned) {
-      B200_CUDA(cudaStreamSynchronize(st));
+      B200_CUDA(sync_fetch(st));
       // head-room: an rMCL loop alternates between a few sizes, and re-allocating tens of GB
       // costs ~1 s; grow by at least 2x the old capacity (falls back to the exact size below)
       const size_t old_cap = c.arena_cap;
@@ -2305,8 +2354,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       }
       int* d_ticket_slot = nullptr;  // at most team_max tickets per slot, usually ~1.2 per slot
       int h_tickets = 0;
-      B200_CUDA(cudaMemcpyAsync(&h_tickets, d_itemoff + nslots, sizeof(int), cudaMemcpyDeviceToHost, st));
-      B200_CUDA(cudaStreamSynchronize(st));
+      B200_CUDA(d2h_small(&h_tickets, d_itemoff + nslots, sizeof(int), st));
+      B200_CUDA(sync_fetch(st));
       B200_CUDA(T.alloc(&d_ticket_slot, (size_t)h_tickets + 1));
       k_fill_tickets<<<(nslots + 255) / 256, 256, 0, st>>>(d_itemoff, nslots, d_ticket_slot);
       launches += 3;
@@ -2342,8 +2391,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ++launches;
     if (d_prof) {
       unsigned long long h[8];
-      B200_CUDA(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
-      B200_CUDA(cudaStreamSynchronize(st));
+      B200_CUDA(d2h_small(h, d_prof, sizeof h, st));
+      B200_CUDA(sync_fetch(st));
       fprintf(stderr, "[b200 prof] k_num_bitmap Mcycles/CTA: bitmap %.2f prefix %.2f emit %.2f products %.2f epilogue %.2f (grid %d)\n",
               h[0] / 1e6 / grid, h[1] / 1e6 / grid, h[2] / 1e6 / grid, h[3] / 1e6 / grid, h[4] / 1e6 / grid, grid);
 
@@ -2367,11 +2416,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ++launches;
     unsigned long long h_cur[2] = {0, 0};
     long long h_kept_total = 0;
-    B200_CUDA(cudaMemcpyAsync(h_cur, d_cursor, 2 * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(&h_kept_total, C->rowptr + m, sizeof(long long),
-                              cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(d2h_small(h_cur, d_cursor, 2 * sizeof(unsigned long long), st));
+    B200_CUDA(d2h_small(&h_kept_total, C->rowptr + m, sizeof(long long), st));
+    B200_CUDA(sync_fetch(st));
     nnz_out = h_kept_total;
     if (chaos) {
       long long bits = (long long)h_cur[1];
@@ -2398,13 +2445,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     const int grid = std::min((m + 255) / 256, c.sm_count * 8);
     k_bin_aggregate<<<grid, 256, 0, st>>>(d_bin, m, A.rowptr, row_lo, d_flops, nullptr, d_agg);
     k_bin_aggregate<<<grid, 256, 0, st>>>(d_nbin, m, A.rowptr, row_lo, d_flops, d_cnt, d_agg + 48);
-    B200_CUDA(cudaMemcpyAsync(h_agg, d_agg, sizeof h_agg, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(d2h_small(h_agg, d_agg, sizeof h_agg, st));
 
   }
 
 
 
-  B200_CUDA(cudaStreamSynchronize(st));
+  B200_CUDA(sync_fetch(st));
   B200_CUDA(cudaGetLastError());
   T.keep(C->rowptr);
   T.keep(C->col);
