@@ -427,8 +427,9 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     product out as malloc'd host int CSR row blocks handed to a callback that owns and frees
     them.  nnz(C) = 9.7e9 exceeds the reference's `int` CSR, so the library cuts row blocks where
     the intermediate-product prefix reaches 2e9 (an upper bound of a block's nnz)
-    and overlaps the download of block b with the computation of block b+1.  A rank passes its
-    own row range as IA + lo (offsets stay absolute, as in the reference's kernels)."""
+    and overlaps the download of block b with the computation of block b+1.  With N > 1 ranks
+    each rank walks its own row range with the upload / row-block product / row-block download
+    sequence instead (same buffers, no overlap)."""
     from sparse_matrix_with_flops_b200 import _lib
     ip, dp = _lib.c_int_p, _lib.c_double_p
     h2d = d2h = nblk = 0
@@ -444,7 +445,7 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
             lib.b200_host_free(C.cast(p, C.c_void_p))
         return 0
 
-    def one():
+    def one_streamed():
         nonlocal h2d, d2h, nblk
         d2h = nblk = 0
         h2d = 4 * (hi - lo + 1) + 12 * A.nnz + (0 if same else 4 * (A.rows + 1) + 12 * A.nnz)
@@ -453,26 +454,66 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
             A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
             hi - lo, A.cols, A.cols, 0, sink, None))
 
-    one()  # warm-up (page-faults the pools, loads the kernels)
+    # N > 1: the sequence measured on 2 / 4 / 8 GPUs in profiles/ — CSR::toGpuCSR of the whole
+    # matrix, gpuSpMMWrapper on this rank's row blocks, CSR::toCpuCSR of each block
+    prefix = host_flops_prefix(A)
+    mine = int(prefix[hi] - prefix[lo])
+    nblk_seq = max(1, -(-mine // 2_000_000_000))
+    cuts = smf.arrayEqualPartition64((prefix[lo:hi + 1] - prefix[lo]).astype(np.int64), nblk_seq) + lo
+
+    def one_sequential():
+        nonlocal h2d, d2h, nblk
+        dA = A.toGpuCSR()
+        h2d = 4 * (A.rows + 1) + 12 * A.nnz
+        d2h = nblk = 0
+        for b in range(nblk_seq):
+            r0, r1 = int(cuts[b]), int(cuts[b + 1])
+            if r1 <= r0:
+                continue
+            dC = smf.gpuSpMMWrapper(dA, dA, r0, r1)
+            IC, JC, Cv, nnzC = ip(), ip(), dp(), C.c_int(0)
+            _lib.check(lib.b200_csr_download_rows(dC.handle, 0, r1 - r0, C.byref(IC), C.byref(JC),
+                                                  C.byref(Cv), C.byref(nnzC)))
+            dC.deviceDispose()
+            sink(None, r0, r1, IC, JC, Cv, nnzC.value)
+        dA.deviceDispose()
+
+    one = one_streamed if world == 1 else one_sequential
+    api = ("b200_spgemm_csr_stream (host int CSR in, malloc'd host int CSR row blocks out through a callback)"
+           if world == 1 else
+           "b200_csr_upload + b200_spgemm_device_rows + b200_csr_download_rows per row block (host malloc'd int CSR in/out)")
+
+    # A rank whose call fails still takes part in every collective below (no deadlock); the leg
+    # is then reported as failed instead of taking the whole bench line down.
+    err = None
+    try:
+        one()  # warm-up (page-faults the pools, fills the host block cache, loads the kernels)
+    except Exception as e:  # noqa: BLE001
+        err = repr(e)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        one()
+        if err is None:
+            try:
+                one()
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
     barrier()
     sec = (time.perf_counter() - t0) / args.e2e_steps
     import torch
     import torch.distributed as dist
-    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    t = torch.tensor([sec, 1.0 if err else 0.0], dtype=torch.float64, device="cuda")
     io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    if float(t[1]) > 0:
+        return {"value": None, "unit": UNIT, "error": err or "another rank failed"}
     sec = float(t[0])
     return {"value": 2.0 * P / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
             "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
             "warmup": 1, "row_blocks": nblk,
-            "api": "b200_spgemm_csr_stream (host int CSR in, malloc'd host int CSR row blocks out through "
-                   "a callback), wall clock incl. H2D + D2H"}
+            "api": api + ", wall clock incl. H2D + D2H"}
 
 
 def main():
