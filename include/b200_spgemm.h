@@ -205,7 +205,15 @@ int b200_synth_stencil27(int gx, int gy, int gz, int* rows, int** IA, int** JA, 
 int b200_synth_planted(int n, int nblocks, int intra, int inter, unsigned long long seed,
                        int* rows, int** IA, int** JA, double** A, long long* nnz,
                        int** labels);
+/* Releases a malloc()'d block returned by this library.  Large blocks (>= 64 MB) are kept for
+ * the next download instead of going back to the OS, up to B200_HOST_CACHE_GB (environment;
+ * default a quarter of the physical memory, at most 64 GB; 0 = never keep): the first touch of
+ * a fresh 10 GB block costs more than copying into it.  free() on such blocks stays legal. */
 void b200_host_free(void* p);
+/* Bytes and blocks currently kept by b200_host_free, and the limit in force. */
+int b200_host_cache_info(long long* bytes, int* blocks, long long* limit_bytes);
+/* Gives every kept block back to the OS (b200_finalize does the same). */
+int b200_host_cache_drop(void);
 
 #ifdef __cplusplus
 }

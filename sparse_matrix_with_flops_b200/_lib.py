@@ -106,6 +106,8 @@ SIGNATURES = {
                                      C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p),
                                      c_ll_p, C.POINTER(c_int_p)]),
     "b200_host_free": (None, [C.c_void_p]),
+    "b200_host_cache_info": (C.c_int, [c_ll_p, c_int_p, c_ll_p]),
+    "b200_host_cache_drop": (C.c_int, []),
 }
 
 _lib = None

@@ -448,6 +448,20 @@ void b200_host_free(void* p) {
   if (p && !host_cache().give(p)) free(p);
 }
 
+int b200_host_cache_info(long long* bytes, int* blocks, long long* limit_bytes) {
+  HostCache& h = host_cache();
+  std::lock_guard<std::mutex> lk(h.mu);
+  if (bytes) *bytes = (long long)h.total;
+  if (blocks) *blocks = (int)h.blocks.size();
+  if (limit_bytes) *limit_bytes = (long long)h.cap_limit();
+  return B200_OK;
+}
+
+int b200_host_cache_drop(void) {
+  host_cache().drop_all();
+  return B200_OK;
+}
+
 int b200_init(int device) {
   Ctx& c = ctx();
   if (c.ready) {

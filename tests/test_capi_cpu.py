@@ -3,6 +3,8 @@ include/b200_spgemm.h declares, refuses to compute without a GPU, and its host-o
 (partition arithmetic, generators) agree with the checker.  No device compute here."""
 import ctypes as C
 import os
+import subprocess
+import sys
 import re
 
 import numpy as np
@@ -37,6 +39,46 @@ def test_no_cpu_fallback(smf):
         A.flops_spmm(A)
     with pytest.raises(smf._lib.B200Error):
         A.spmm_blocks(A, lambda lo, hi, blk: 0)
+
+
+def test_host_block_cache_policy():
+    """b200_host_free keeps large malloc blocks up to B200_HOST_CACHE_GB (smallest evicted first,
+    a block smaller than everything kept is not worth an eviction), frees small ones, and
+    B200_HOST_CACHE_GB=0 turns it off.  Host logic only; runs in a subprocess because the limit
+    is read once."""
+    prog = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from sparse_matrix_with_flops_b200 import _lib
+lib = _lib.load(); libc = C.CDLL(None)
+libc.malloc.restype = C.c_void_p; libc.malloc.argtypes = [C.c_size_t]
+def info():
+    b, n, l = C.c_longlong(), C.c_int(), C.c_longlong()
+    assert lib.b200_host_cache_info(C.byref(b), C.byref(n), C.byref(l)) == 0
+    return b.value, n.value, l.value
+MB = 1 << 20
+out = []
+for mb in (100, 150, 80, 1):
+    lib.b200_host_free(C.c_void_p(libc.malloc(mb * MB)))
+    out.append(info()[:2])
+lib.b200_host_free(None)
+lib.b200_host_cache_drop()
+out.append(info())
+print(out)
+""" % ROOT
+    def run(gb):
+        env = dict(os.environ, B200_HOST_CACHE_GB=gb)
+        r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0, r.stderr
+        return eval(r.stdout.strip())
+    MB = 1 << 20
+    a = run("0.2")                       # 214 MB
+    assert a[0][1] == 1 and a[0][0] >= 100 * MB
+    assert a[1][1] == 1 and 150 * MB <= a[1][0] < 160 * MB      # the 100 MB block made room
+    assert a[2] == a[1] and a[3] == a[1]                        # 80 MB not kept, 1 MB freed
+    assert a[4][:2] == (0, 0) and abs(a[4][2] - 0.2 * (1 << 30)) < 2
+    z = run("0")
+    assert all(x[:2] == (0, 0) for x in z)
 
 
 def test_product_does_not_touch_the_oracle():
