@@ -682,13 +682,15 @@ static int stream_blocks(const DevCSR& A, const DevCSR& B, long long block_produ
     memset(&st, 0, sizeof st);
     int rc = run_pipeline(A, B, lo, hi, MODE_SPGEMM, &dC, nullptr, prof ? &st : nullptr);
     const double t1 = now();
-    if (!rc) rc = download_prepare(dC, 0, hi - lo, &hb);
-    const double t2 = now();
-    // block b-1 has had the whole computation of block b to arrive; start block b's transfer
-    // before the callback sees block b-1, so that the copy engine never waits for the callback
+    // block b-1 has had the whole computation of block b to arrive.  Only when it has landed
+    // are block b's row offsets fetched (their copy shares the device-to-host copy engine with
+    // the download and would wait for it anyway), and block b's transfer starts before the
+    // callback sees block b-1, so that the copy engine never waits for the callback.
     const int rc_land = land();
-    const double t3 = now();
+    const double t2 = now();
     if (!rc) rc = rc_land;
+    if (!rc) rc = download_prepare(dC, 0, hi - lo, &hb);
+    const double t3 = now();
     if (!rc) rc = dl.submit(dC, hb);
     if (rc) {
       release(dC); hb.drop();
@@ -704,7 +706,7 @@ static int stream_blocks(const DevCSR& A, const DevCSR& B, long long block_produ
               st.ms_total, st.ms_flops, st.ms_symbolic, st.ms_numeric, st.ms_other, kern);
     }
     if (prof)
-      fprintf(stderr, "[b200 stream] rows %d-%d nnz %lld: compute %.1f prepare %.1f wait-for-previous %.1f callback %.1f ms; host cache %ld hits %ld misses\n",
+      fprintf(stderr, "[b200 stream] rows %d-%d nnz %lld: compute %.1f wait-for-previous %.1f prepare %.1f callback %.1f ms; host cache %ld hits %ld misses\n",
               lo, hi, (long long)hb.cnt, t1 - t0, t2 - t1, t3 - t2, now() - t3, host_cache().hits, host_cache().misses);
     if (rc) { land(); if (done.on) { done.hb.drop(); done.on = false; } return rc; }
     lo = hi;
