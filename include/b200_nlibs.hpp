@@ -417,6 +417,22 @@ inline CSR rmclInit(COO& cooAt) {
   return Mt;
 }
 
+// rmclInit with the COO -> CSR build done on the device (b200_coo_to_csr): returns a DEVICE CSR
+// (toCpuCSR() brings it back).  `dedup` also drops repeated (row, col) pairs, which the host
+// version must not be given (SURVEY.md §8c input hazards).
+inline CSR rmclInitDevice(const COO& cooAt, bool dedup = false) {
+  b200_ensure_init();
+  CSR d;
+  d.rows = cooAt.rows; d.cols = cooAt.cols;
+  b200_check(b200_coo_to_csr(cooAt.cooRowIndex, cooAt.cooColIndex, NULL, cooAt.nnz, cooAt.rows, cooAt.cols,
+                             B200_COO_SELF_LOOPS | B200_COO_NORMALISE | (dedup ? B200_COO_DEDUP : 0), &d.device),
+             "b200_coo_to_csr");
+  long long z = 0;
+  b200_check(b200_csr_info(d.device, NULL, NULL, &z), "b200_csr_info");
+  d.nnz = (int)z;
+  return d;
+}
+
 // RMCL (nlibs/qrmcl.cc:136-164) from an in-memory COO instead of a file name (file ingest is the
 // next row of SURVEY.md §8f); every RunOptions value runs the B200 path.
 inline CSR RMCL(COO& cooAt, int maxIters, RunOptions runOptions = B200, double eps = 0.0,

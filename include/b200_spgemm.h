@@ -146,6 +146,19 @@ int b200_csr_download(b200_csr_t h, int** I, int** J, double** V, int* nnz);
 int b200_csr_download_rows(b200_csr_t h, int row_lo, int row_hi, int** I, int** J, double** V,
                            int* nnz);
 int b200_csr_free(b200_csr_t h);
+/* Edge list (COO, host arrays of nnz entries; val may be NULL = all ones) to a device CSR, built
+ * on the device.  Replaces COO::addSelfLoopIfNeeded (nlibs/COO.cc:160-188), COO::makeOrdered +
+ * COO::toCSR (COO.cc:222-235), orderedAndDuplicatesRemoving (COO.cc:237-266) and
+ * CSR::averAndNormRowQValue (nlibs/CSR.cc:88-95); B200_COO_SELF_LOOPS | B200_COO_NORMALISE is
+ * rmclInit (nlibs/qrmcl.cc:126-134).  Entries come out ordered by (row, column); of repeated
+ * (row, column) pairs the first in input order stays when B200_COO_DEDUP is set (without it they
+ * all stay, which the multiplication entry points do not accept: SURVEY.md §8c input hazards).
+ * Indices outside the matrix are an error. */
+#define B200_COO_DEDUP 1
+#define B200_COO_SELF_LOOPS 2
+#define B200_COO_NORMALISE 4
+int b200_coo_to_csr(const int* rowIndex, const int* colIndex, const double* val, long long nnz,
+                    int rows, int cols, int flags, b200_csr_t* out);
 /* CSR::makeOrdered (nlibs/CSR.cc:73-86) on the device: sort every row by column, in place. */
 int b200_csr_sort_rows(b200_csr_t h);
 /* Device pointers of a handle (row offsets are 64-bit on the device). */

@@ -6,11 +6,13 @@ interface on top of it.  Importing the package does not need a GPU; the first ca
 computes does, and fails loudly without one (there is no CPU fallback).
 """
 from . import _lib
-from .csr import (CSR, DeviceCSR, RMCL, arrayEqualPartition64, comm_destroy, comm_init,
+from .csr import (COO_DEDUP, COO_NORMALISE, COO_SELF_LOOPS, CSR, DeviceCSR, RMCL,
+                  arrayEqualPartition64, comm_destroy, comm_init, cooToGpuCSR, rmclInitDevice,
                   comm_unique_id, flops_prefix, gpuRmclIter, gpuRmclIterSharded, gpuRmclOneStep,
                   gpuSpMMWrapper, init, rmclInit, synth_planted, synth_rmat, synth_stencil27)
 
-__all__ = ["CSR", "DeviceCSR", "RMCL", "arrayEqualPartition64", "comm_destroy", "comm_init",
+__all__ = ["COO_DEDUP", "COO_NORMALISE", "COO_SELF_LOOPS", "cooToGpuCSR", "rmclInitDevice",
+           "CSR", "DeviceCSR", "RMCL", "arrayEqualPartition64", "comm_destroy", "comm_init",
            "comm_unique_id", "flops_prefix", "gpuRmclIter", "gpuRmclIterSharded",
            "gpuRmclOneStep", "gpuSpMMWrapper", "init", "rmclInit", "synth_planted", "synth_rmat",
            "synth_stencil27", "_lib"]

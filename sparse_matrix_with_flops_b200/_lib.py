@@ -80,6 +80,8 @@ SIGNATURES = {
                                          C.POINTER(c_int_p), C.POINTER(c_double_p), c_int_p]),
     "b200_csr_free": (C.c_int, [csr_t]),
     "b200_csr_sort_rows": (C.c_int, [csr_t]),
+    "b200_coo_to_csr": (C.c_int, [c_int_p, c_int_p, c_double_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(csr_t)]),
     "b200_csr_device_ptrs": (C.c_int, [csr_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p)]),
     "b200_spgemm_device": (C.c_int, [csr_t, csr_t, C.POINTER(csr_t), C.POINTER(Stats)]),

@@ -310,6 +310,31 @@ def rmclInit(rows_idx, cols_idx, n):
     return CSR(vals, c.astype(np.int32), rowPtr.astype(np.int32), n, n)
 
 
+COO_DEDUP, COO_SELF_LOOPS, COO_NORMALISE = 1, 2, 4
+
+
+def cooToGpuCSR(rows_idx, cols_idx, vals, rows, cols, flags=0):
+    """COO -> device CSR built on the device (b200_coo_to_csr): COO::toCSR (nlibs/COO.cc:222-235)
+    plus, by flag, duplicate removal (COO.cc:237-266), addSelfLoopIfNeeded (COO.cc:160-188) and
+    averAndNormRowQValue (nlibs/CSR.cc:88-95).  `vals` may be None (all ones)."""
+    _ensure_init()
+    lib = _lib.load()
+    r = np.ascontiguousarray(rows_idx, dtype=np.int32)
+    c = np.ascontiguousarray(cols_idx, dtype=np.int32)
+    assert r.shape == c.shape and r.ndim == 1
+    v = None if vals is None else np.ascontiguousarray(vals, dtype=np.float64)
+    h = csr_t()
+    check(lib.b200_coo_to_csr(_ip(r), _ip(c), None if v is None else _dp(v), r.shape[0], rows, cols,
+                              flags, C.byref(h)))
+    return DeviceCSR(h)
+
+
+def rmclInitDevice(rows_idx, cols_idx, n, dedup=False):
+    """rmclInit (nlibs/qrmcl.cc:126-134) on the device: self loops, (row, col) order, 1/rowcount."""
+    return cooToGpuCSR(rows_idx, cols_idx, None, n, n,
+                       COO_SELF_LOOPS | COO_NORMALISE | (COO_DEDUP if dedup else 0))
+
+
 def RMCL(Mt0, maxIters=5, eps=0.0):
     """RMCL (nlibs/qrmcl.cc:136-164) with RunOptions::GPU semantics, starting from an
     rmclInit()'ed matrix instead of a file: Mgt = Mt.deepCopy(); loop; return Mt."""

@@ -551,6 +551,32 @@ int b200_csr_upload(const int* I, const int* J, const double* V, int rows, int c
   return B200_OK;
 }
 
+int b200_coo_to_csr(const int* rowIndex, const int* colIndex, const double* val, long long nnz,
+                    int rows, int cols, int flags, b200_csr_t* out) {
+  B200_REQUIRE_INIT();
+  if (!out || rows < 0 || cols < 0 || nnz < 0 || (nnz && (!rowIndex || !colIndex)) || (flags & ~7)) {
+    set_error("bad COO arguments");
+    return B200_ERR_BAD_ARG;
+  }
+  Temps T;
+  int *d_row = nullptr, *d_col = nullptr;
+  double* d_val = nullptr;
+  B200_CUDA(T.alloc(&d_row, (size_t)nnz));
+  B200_CUDA(T.alloc(&d_col, (size_t)nnz));
+  int rc = h2d_staged(d_row, rowIndex, (size_t)nnz * sizeof(int));
+  if (!rc) rc = h2d_staged(d_col, colIndex, (size_t)nnz * sizeof(int));
+  if (!rc && val && !(flags & B200_COO_NORMALISE)) {   // normalised values do not depend on the input's
+    B200_CUDA(T.alloc(&d_val, (size_t)nnz));
+    rc = h2d_staged(d_val, val, (size_t)nnz * sizeof(double));
+  }
+  if (rc) return rc;
+  b200_csr* h = new b200_csr();
+  rc = coo_build_device(d_row, d_col, d_val, nnz, rows, cols, flags, &h->d);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return B200_OK;
+}
+
 int b200_csr_info(b200_csr_t h, int* rows, int* cols, long long* nnz) {
   if (!h) { set_error("null handle"); return B200_ERR_BAD_ARG; }
   if (rows) *rows = h->d.rows;

@@ -136,6 +136,11 @@ struct Temps {
 // mode of the row pipeline
 enum Mode { MODE_SPGEMM = 0, MODE_RMCL = 1 };
 
+// COO -> CSR on the device (ingest.cu); flags: 1 drop repeated pairs, 2 add missing self loops,
+// 4 values = 1 / rowcount
+int coo_build_device(const int* d_row, const int* d_col, const double* d_val, long long nnz, int rows,
+                     int cols, int flags, DevCSR* out);
+
 // Core pipeline (spgemm.cu): C = A[row_lo:row_hi) x B, or the fused rMCL step.
 int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode,
                  DevCSR* C, double* chaos, b200_stats* stats);

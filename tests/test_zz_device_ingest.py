@@ -1,0 +1,109 @@
+"""Device COO -> CSR build (b200_coo_to_csr, SURVEY.md §8f rank 1: the step just before the hot
+path) against the checker's restatement of rmclInit (nlibs/qrmcl.cc:126-134) and against numpy
+restatements of COO::toCSR / orderedAndDuplicatesRemoving (nlibs/COO.cc:222-266).  Bit-exact:
+row offsets, columns and values (1/rowcount is one correctly rounded division on both sides).
+
+The GPU work runs in a child process, so that a fault in this new entry point cannot take the
+CUDA context of the other parity tests with it.
+
+STATUS: written after round 1's GPU budget was spent — it has been compiled for sm_100a but has
+not run on a B200 yet, hence the non-strict xfail marker (remove it after the first green run)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import os, sys
+import numpy as np
+ROOT = %r
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as ol
+import sparse_matrix_with_flops_b200 as smf
+smf.init(0)
+
+def same(dev, I, J, V, what):
+    h = dev.toCpuCSR()
+    dev.deviceDispose()
+    assert np.array_equal(h.rowPtr, I), what + ": rowPtr"
+    assert np.array_equal(h.colInd, J), what + ": colInd"
+    assert np.array_equal(h.values, V), what + ": values"
+
+# 1. the reference's own fixture (tests/golden: t2.snap through the reference's rmclInit)
+g = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+same(smf.rmclInitDevice(g["t2_edges_r"], g["t2_edges_c"], 3), g["t2_A_I"], g["t2_A_J"], g["t2_A_V"], "t2 golden")
+
+rng = np.random.default_rng(11)
+def edges(n, m, diag_frac=0.3, empty_from=None):
+    r = rng.integers(0, n if empty_from is None else empty_from, m)
+    c = rng.integers(0, n, m)
+    d = rng.integers(0, n if empty_from is None else empty_from, int(n * diag_frac))
+    r = np.concatenate([r, d]); c = np.concatenate([c, d])
+    return r.astype(np.int32), c.astype(np.int32)
+
+# 2. duplicate-free edge lists against the checker's rmclInit (with and without existing diagonals,
+#    with vertices that only get their self loop)
+for n, m, ef in ((1, 0, None), (7, 5, None), (1000, 8000, None), (5000, 20000, 3000), (1 << 16, 1 << 20, None)):
+    r, c = edges(n, m, empty_from=ef)
+    key = np.unique(r.astype(np.int64) * n + c)
+    rng.shuffle(key)
+    ur, uc = (key // n).astype(np.int32), (key %% n).astype(np.int32)
+    want = ol.o_rmcl_init(ur, uc, n)
+    same(smf.rmclInitDevice(ur, uc, n), want.I, want.J, want.V, "rmclInit n=%%d" %% n)
+    # 3. the same list WITH its repeated pairs and the dedup flag
+    same(smf.rmclInitDevice(r, c, n, dedup=True), want.I, want.J, want.V, "rmclInit dedup n=%%d" %% n)
+
+# 4. COO::toCSR alone: values travel with their entries, rectangular shape, no self loops
+rows, cols, m = 300, 900, 5000
+key = rng.choice(rows * cols, m, replace=False)
+r, c = (key // cols).astype(np.int32), (key %% cols).astype(np.int32)
+v = rng.random(m)
+o = np.lexsort((c, r))
+I = np.zeros(rows + 1, np.int32); np.add.at(I, r + 1, 1); I = np.cumsum(I).astype(np.int32)
+same(smf.cooToGpuCSR(r, c, v, rows, cols, 0), I, c[o], v[o], "toCSR")
+same(smf.cooToGpuCSR(r, c, None, rows, cols, 0), I, c[o], np.ones(m), "toCSR, no values")
+
+# 5. repeated pairs: the first in input order stays (orderedAndDuplicatesRemoving)
+r2 = np.concatenate([r, r[:700]]); c2 = np.concatenate([c, c[:700]]); v2 = np.concatenate([v, -v[:700]])
+same(smf.cooToGpuCSR(r2, c2, v2, rows, cols, smf.COO_DEDUP), I, c[o], v[o], "dedup keeps the first")
+
+# 6. self loops without normalisation carry 1.0 (COO.cc:183) and do not double an existing diagonal
+n = 50
+r = np.array([0, 0, 3, 3, 7], np.int32); c = np.array([0, 5, 3, 1, 2], np.int32); v = np.array([9., 8., 7., 6., 5.])
+d = smf.cooToGpuCSR(r, c, v, n, n, smf.COO_SELF_LOOPS).toCpuCSR()
+assert d.nnz == 5 + n - 2
+assert list(d.colInd[d.rowPtr[0]:d.rowPtr[1]]) == [0, 5] and list(d.values[d.rowPtr[0]:d.rowPtr[1]]) == [9., 8.]
+assert list(d.colInd[d.rowPtr[3]:d.rowPtr[4]]) == [1, 3] and list(d.values[d.rowPtr[3]:d.rowPtr[4]]) == [6., 7.]
+assert list(d.colInd[d.rowPtr[7]:d.rowPtr[8]]) == [2, 7] and list(d.values[d.rowPtr[7]:d.rowPtr[8]]) == [5., 1.]
+
+# 7. error convention: an index outside the matrix
+try:
+    smf.cooToGpuCSR(np.array([0, 60], np.int32), np.array([1, 1], np.int32), None, n, n, 0)
+    raise SystemExit("out-of-range index accepted")
+except smf._lib.B200Error as e:
+    assert e.code == 1
+
+# 8. the device-built matrix drives the hot path: rMCL from it equals rMCL from the host-built one
+n = 4096
+r, c = edges(n, 40000)
+key = np.unique(np.concatenate([r.astype(np.int64) * n + c, c.astype(np.int64) * n + r]))
+ur, uc = (key // n).astype(np.int32), (key %% n).astype(np.int32)
+dM = smf.rmclInitDevice(ur, uc, n)
+hM = smf.rmclInit(ur, uc, n)
+a, _, ha = smf.gpuRmclIter(4, hM, hM)
+dM_host = dM.toCpuCSR(); dM.deviceDispose()
+b, _, hb = smf.gpuRmclIter(4, dM_host, dM_host)
+assert np.array_equal(a.rowPtr, b.rowPtr) and np.array_equal(a.colInd, b.colInd) and np.array_equal(a.values, b.values)
+print("INGEST-OK")
+''' % ROOT
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="b200_coo_to_csr was written after round 1's GPU budget was spent: "
+                                        "compiled for sm_100a, not yet run on a B200")
+def test_device_coo_build_matches_the_checker():
+    out = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "INGEST-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
