@@ -15,12 +15,14 @@ row offsets → numeric (sorted columns), result left in HBM.
               cost (arrayEqualPartition64 on products + a per-row charge), rank r computes
               block r against the full B; no collective on the data path; total work fixed =>
               "scaling": "strong".
-* e2e         the same product through the reference-facing call sequence with HOST buffers
-              (toGpuCSR -> gpuSpMMWrapper -> toCpuCSR: b200_csr_upload, b200_spgemm_device_rows,
-              b200_csr_download_rows; malloc'd int CSR in and out), H2D and D2H copies inside
-              the timed region.  nnz(C) = 9.7e9 exceeds the reference's `int` CSR, so the
-              caller walks row blocks cut so that every block's products (an upper bound of
-              its nnz) fit an int.
+* e2e         the same product through the reference-facing host-buffer call: malloc'd int
+              CSR in, malloc'd int CSR out, H2D and D2H copies inside the timed region.
+              nnz(C) = 9.7e9 exceeds the reference's `int` CSR, so the result arrives as
+              consecutive row blocks whose products (an upper bound of their nnz) fit an int
+              (SURVEY.md §7): b200_spgemm_csr_stream at N = 1 (the library cuts the blocks and
+              overlaps the download of one with the computation of the next), the
+              toGpuCSR -> gpuSpMMWrapper(row block) -> toCpuCSR(row block) sequence per rank
+              at N > 1.  The caller hands every block back with b200_host_free.
 * roofline    the kernel with the largest share of the step: algorithmic bytes of the rows it
               processed ÷ its CUDA-event duration (b200_stats.ms_*_bin), against the measured
               HBM copy bandwidth of MEASURED_PEAKS.json.
