@@ -64,6 +64,8 @@ typedef struct b200_stats {
   long long num_bin_products[16], num_bin_nnzA[16], num_bin_nnzC[16];
   int part_kernel;     /* 1: the bitmap bin's numeric pass ran as k_num_bitmap_part */
   int part_count;      /* column parts it used */
+  int range_items;     /* work items of the on-chip numeric pass (k_num_items); 0: not used */
+  int ranges;          /* static column ranges it planned with */
 } b200_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -72,6 +74,9 @@ typedef struct b200_stats {
  * B200_ERR_NO_DEVICE when no CUDA device is present: there is no CPU fallback. */
 int b200_init(int device);
 int b200_finalize(void);
+/* Developer switches (B200_* environment variables) are read once by b200_init;
+ * this re-reads them (tests and A/B measurements change them between calls). */
+int b200_options_reload(void);
 const char* b200_last_error(void);
 /* The CUDA stream (a cudaStream_t) every kernel of this library is launched on, so that a
  * harness can bracket calls with its own CUDA events. */

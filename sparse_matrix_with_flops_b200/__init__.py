@@ -9,10 +9,10 @@ from . import _lib
 from .csr import (COO_DEDUP, COO_NORMALISE, COO_SELF_LOOPS, CSR, DeviceCSR, RMCL,
                   arrayEqualPartition64, comm_destroy, comm_init, cooToGpuCSR, rmclInitDevice,
                   comm_unique_id, flops_prefix, gpuRmclIter, gpuRmclIterSharded, gpuRmclOneStep,
-                  gpuSpMMWrapper, init, rmclInit, synth_planted, synth_rmat, synth_stencil27)
+                  gpuSpMMWrapper, init, reload_options, rmclInit, synth_planted, synth_rmat, synth_stencil27)
 
 __all__ = ["COO_DEDUP", "COO_NORMALISE", "COO_SELF_LOOPS", "cooToGpuCSR", "rmclInitDevice",
            "CSR", "DeviceCSR", "RMCL", "arrayEqualPartition64", "comm_destroy", "comm_init",
            "comm_unique_id", "flops_prefix", "gpuRmclIter", "gpuRmclIterSharded",
-           "gpuRmclOneStep", "gpuSpMMWrapper", "init", "rmclInit", "synth_planted", "synth_rmat",
+           "gpuRmclOneStep", "gpuSpMMWrapper", "init", "reload_options", "rmclInit", "synth_planted", "synth_rmat",
            "synth_stencil27", "_lib"]

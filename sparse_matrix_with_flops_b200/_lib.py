@@ -41,6 +41,8 @@ class Stats(C.Structure):
         ("num_bin_nnzC", C.c_longlong * 16),
         ("part_kernel", C.c_int),
         ("part_count", C.c_int),
+        ("range_items", C.c_int),
+        ("ranges", C.c_int),
     ]
 
     def as_dict(self):
@@ -55,6 +57,7 @@ class Stats(C.Structure):
 SIGNATURES = {
     "b200_init": (C.c_int, [C.c_int]),
     "b200_finalize": (C.c_int, []),
+    "b200_options_reload": (C.c_int, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_stream": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b200_device_info": (C.c_int, [c_int_p, c_ll_p, C.c_char_p, C.c_int]),

@@ -31,6 +31,13 @@ def init(device=0):
     _inited["device"] = int(device)
 
 
+def reload_options():
+    """b200_options_reload: re-read the B200_* developer switches from the environment (the
+    library reads them once, in b200_init)."""
+    _ensure_init()
+    check(_lib.load().b200_options_reload())
+
+
 def _ensure_init():
     if _inited["device"] is None:
         init(0)

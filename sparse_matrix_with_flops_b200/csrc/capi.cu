@@ -493,7 +493,13 @@ int b200_init(int device) {
   B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long thr = ~0ull;
   B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  load_tunables(&c.tun);
   c.ready = true;
+  return B200_OK;
+}
+
+int b200_options_reload(void) {
+  load_tunables(&ctx().tun);
   return B200_OK;
 }
 
@@ -673,7 +679,7 @@ static int stream_blocks(const DevCSR& A, const DevCSR& B, long long block_produ
     B200_CUDA(cudaStreamSynchronize(c.stream));
   }
   Downloader& dl = downloader();
-  const bool prof = getenv("B200_PROF") != nullptr;
+  const bool prof = ctx().tun.prof;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   struct Flight { bool on = false; DevCSR dev; HostBlock hb; int lo = 0, hi = 0; } fly, done;
   // wait for the block in flight and free its device copy; it becomes `done`

@@ -32,8 +32,34 @@ struct b200_csr {
 };
 namespace b200 {
 
+// Developer switches.  Read from the environment ONCE, by b200_init and by
+// b200_options_reload — never on the per-call path.
+struct Tunables {
+  bool force_wide = false;   // B200_FORCE_WIDE: treat B as too wide for any shared-memory bitmap
+  bool parts4 = false;       // B200_PARTS4: 4 x 256-thread CTAs / SM geometry of the part kernel
+  bool no_parts = false;     // B200_NO_PARTS: whole-row numeric bitmap kernel
+  bool on_chip = false;      // B200_ON_CHIP: heavy rows through the range-item kernel (ranges.cuh);
+                             // implied by B200_DETERMINISTIC.  Default off: measured slower than the
+                             // part kernel (global RED) on R-MAT scale 20, see DESIGN.md §3b
+  bool prof = false;         // B200_PROF: per-phase diagnostics on stderr
+  int l2[5] = {2, 1, 0, 1, 0};  // B200_L2POL=acc,ocol,bgather,bmstore,demote (L2Prio values)
+  long long sym_big_from = -1;  // B200_SYM_BIG_FROM, B200_NUM_BIG_FROM, B200_LIGHT_P: bin cuts (-1: default)
+  int num_big_from = -1;
+  long long light_p = -1;
+  long long team_products = 98304;  // B200_TEAM_P, B200_TEAM_MAX: team sizing of the part kernel
+  int team_max = 64;
+  int ranges = 64;      // B200_RANGES: static column ranges of the on-chip numeric pass (2..64)
+  int chunk_min = 96;   // B200_CHUNK_MIN: items whose expected B-row segments are shorter do not
+                        // commit in A-entry order (a barrier per segment) but by tag arbitration
+  bool no_tag = false;  // B200_NO_TAG: ... or with global RED instead (A/B switch)
+  bool deterministic = false;  // B200_DETERMINISTIC: every on-chip item in A-entry order (bit-exact,
+                               // reproducible; slower on rows with thousands of short segments)
+};
+void load_tunables(Tunables* t);
+
 struct Ctx {
   bool ready = false;
+  Tunables tun;
   int device = -1;
   int sm_count = 0;
   size_t smem_optin = 0;

@@ -161,6 +161,11 @@ __device__ __forceinline__ double ldg_hint(const double* a, unsigned long long p
   asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
   return v;
 }
+__device__ __forceinline__ unsigned long long ldg_hint(const unsigned long long* a, unsigned long long pol) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ ulonglong2 ldg_hint(const ulonglong2* a, unsigned long long pol) {
   ulonglong2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
@@ -910,10 +915,13 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
              unsigned long long* __restrict__ gscratch, unsigned long long* __restrict__ bm_store,
              int store_rows, int* __restrict__ bm_slot, int* __restrict__ rownnz,
              int nparts, int wpp, int* __restrict__ partcnt, int* __restrict__ work_counter,
-             L2Modes l2) {
+             L2Modes l2, const unsigned char* __restrict__ wr, int R, int* __restrict__ rcnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_pc[BT / 32][PARTS_WHOLE];
   __shared__ int s_idx;
+  // output columns per static column range (ranges.cuh), for the rows whose bitmap is stored
+  __shared__ int s_rc[64];
+  if (threadIdx.x < 64) s_rc[threadIdx.x] = 0;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
                                    : gscratch + (size_t)blockIdx.x * nw64;
@@ -935,16 +943,28 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
     // multiple of BT, so the part of a sweep step is the same for the whole CTA
     int pc[PARTS_WHOLE] = {0, 0, 0, 0};
     unsigned long long* dst = (bm_store && idx < store_rows) ? bm_store + (size_t)idx * nw64 : nullptr;
+    const bool want_rc = rcnt != nullptr && dst != nullptr;
     for (int w0 = 0, h = 0, hnext = wpp; w0 < nw64; w0 += BT) {
       const int w = w0 + threadIdx.x;
       if (w0 >= hnext) { ++h; hnext += wpp; }
+      int c = 0;
       if (w < nw64) {
         const unsigned long long x = bm[w];
-        const int c = __popcll(x);
+        c = __popcll(x);
 #pragma unroll
         for (int k = 0; k < PARTS_WHOLE; ++k) pc[k] += (k == h) ? c : 0;
         if (dst) stg_hint(dst + w, x, pol_bm);
         bm[w] = 0ull;
+      }
+      // the 32 words of a warp are consecutive: they lie in one range, or in a few
+      const int wf = w0 + (threadIdx.x & ~31);
+      if (want_rc && wf < nw64) {
+        const int rf = wr[wf], rl = wr[min(nw64 - 1, wf + 31)];
+        const int myr = (rf == rl || w >= nw64) ? rf : (int)wr[w];
+        for (int r = rf; r <= rl; ++r) {
+          const int sr = warp_sum_int(myr == r ? c : 0);
+          if ((threadIdx.x & 31) == 0 && sr) atomicAdd(&s_rc[r], sr);
+        }
       }
     }
     {
@@ -972,6 +992,10 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
     if (threadIdx.x == 0) {
       rownnz[i] = cnt;
       bm_slot[i] = dst ? idx : -1;
+    }
+    if (want_rc && (int)threadIdx.x < R) {  // (s_rc complete: the barrier after s_pc above)
+      rcnt[(size_t)idx * R + threadIdx.x] = s_rc[threadIdx.x];
+      s_rc[threadIdx.x] = 0;
     }
   }
 }
@@ -1697,6 +1721,8 @@ k_gather_rows(int m, const long long* __restrict__ row_off, const int64_t* __res
   }
 }
 
+#include "ranges.cuh"
+
 struct IntToI64 {
   __host__ __device__ __forceinline__ long long operator()(const int& x) const { return (long long)x; }
 };
@@ -1747,6 +1773,28 @@ constexpr int BT_BIG = 1024;
 // ---- small read-backs through mapped pinned memory (common.cuh) -------------------------------
 __global__ void k_readback(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int bytes) {
   for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+void load_tunables(Tunables* t) {
+  *t = Tunables();
+  auto flag = [](const char* k) { const char* e = getenv(k); return e != nullptr && *e != 0; };
+  t->force_wide = flag("B200_FORCE_WIDE");
+  t->parts4 = flag("B200_PARTS4");
+  t->no_parts = flag("B200_NO_PARTS");
+  t->on_chip = flag("B200_ON_CHIP");
+  t->prof = flag("B200_PROF");
+  if (const char* e = getenv("B200_L2POL"))
+    sscanf(e, "%d,%d,%d,%d,%d", &t->l2[0], &t->l2[1], &t->l2[2], &t->l2[3], &t->l2[4]);
+  if (const char* e = getenv("B200_SYM_BIG_FROM")) t->sym_big_from = atoll(e);
+  if (const char* e = getenv("B200_NUM_BIG_FROM")) t->num_big_from = atoi(e);
+  if (const char* e = getenv("B200_LIGHT_P")) t->light_p = atoll(e);
+  if (const char* e = getenv("B200_TEAM_P")) t->team_products = std::max(1LL, atoll(e));
+  if (const char* e = getenv("B200_TEAM_MAX")) t->team_max = std::max(1, atoi(e));
+  if (const char* e = getenv("B200_RANGES")) t->ranges = atoi(e);
+  if (const char* e = getenv("B200_CHUNK_MIN")) t->chunk_min = atoi(e);
+  t->no_tag = flag("B200_NO_TAG");
+  t->deterministic = flag("B200_DETERMINISTIC");
+  if (t->deterministic) t->on_chip = true;
 }
 
 void rb_reset() {
@@ -1904,7 +1952,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   cudaStream_t st = c.stream;
   const int m = row_hi - row_lo;
   const int n = B.cols;
-  int launches = 0;
+  int launches = 0, range_items = 0;
   rb_reset();
   if (stats) memset(stats, 0, sizeof(*stats));
   *C = DevCSR();
@@ -1928,17 +1976,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const size_t smem_cap = c.smem_optin - 1024 - walk_bytes;  // static shared + the walk area
   // B200_FORCE_WIDE=1 (testing switch): behave as if B had too many columns for any
   // shared-memory bitmap, so small inputs exercise the big warp tables and the HBM bitmap
-  const bool force_wide = getenv("B200_FORCE_WIDE") != nullptr;
+  const bool force_wide = c.tun.force_wide;
   const bool sym_smem = !force_wide && bm_bytes <= smem_cap;
   const bool num_smem = !force_wide && bm_pref_bytes <= smem_cap;
   // L2 eviction priorities of the bitmap kernels (B200_L2POL=acc,ocol,bgather,bmstore,demote
   // overrides them: a developer switch for A/B runs)
-  L2Modes l2m = {L2_LAST, L2_FIRST, L2_NORMAL, L2_FIRST, 0};
-  if (const char* e = getenv("B200_L2POL"))
-    sscanf(e, "%d,%d,%d,%d,%d", &l2m.acc, &l2m.ocol, &l2m.bgather, &l2m.bmstore, &l2m.demote);
+  const L2Modes l2m = {c.tun.l2[0], c.tun.l2[1], c.tun.l2[2], c.tun.l2[3], c.tun.l2[4]};
   // Part-wise numeric kernel (SpGEMM, sorted B rows): column parts of <= 8192 bitmap words so
   // that two 512-thread CTAs fit one SM.
-  const bool parts4 = getenv("B200_PARTS4") != nullptr;  // developer switch: 4 x 256 threads / SM
+  const bool parts4 = c.tun.parts4;  // developer switch: 4 x 256 threads / SM
   const int part_words_max = parts4 ? 4096 : 8192;
   const int part_ctas = parts4 ? 4 : 2;
   const size_t walk_part_bytes = parts4 ? sizeof(WalkSmem<256>) : sizeof(WalkSmem<512>);
@@ -1950,16 +1996,25 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   // order — need a column-sorted copy of B when there is more than one part.)
   const bool use_parts = nparts <= PARTS_MAX &&
                          part_ctas * (part_smem + 2048) <= c.smem_optin + 1024 &&
-                         !getenv("B200_NO_PARTS") && !force_wide;
+                         !c.tun.no_parts && !force_wide;
   if (!use_parts) { nparts = 1; wpp = nw64; }
   // symbolic cut: rows of up to 1024 products are cheaper in the (optimistically sized) warp
   // tables at 56 warps / SM than as one bitmap item each (a 27-point stencil row has 729)
   // (with more than two column parts a bitmap row costs one item per part it touches, and the
   // cut moves up: measured on a 4 M-column planted-partition graph, 8 parts: 785 -> 243 ms)
   long long sym_big_from = (sym_smem || use_parts) ? (nparts > 2 ? 4096 : 1024) : 8192;
-  if (const char* e = getenv("B200_SYM_BIG_FROM")) sym_big_from = atoll(e);  // developer switch
+  if (c.tun.sym_big_from >= 0) sym_big_from = c.tun.sym_big_from;  // developer switch
   int num_big_from = (num_smem || use_parts) ? 256 : 2048;
-  if (const char* e = getenv("B200_NUM_BIG_FROM")) num_big_from = atoi(e);  // developer switch
+  if (c.tun.num_big_from >= 0) num_big_from = c.tun.num_big_from;  // developer switch
+
+  // On-chip numeric pass of the heavy rows (ranges.cuh): needs the whole-row symbolic kernel
+  // (it counts the output columns per static range) and the part kernel as its fallback.
+  const int RNG = c.tun.ranges;
+  const bool want_ranges = use_parts && sym_smem && RNG >= 2 && RNG <= RANGES_MAX && c.tun.on_chip;
+  constexpr int ITEM_BT = 512, ITEM_CTAS = 2;
+  const size_t item_dyn = (c.smem_optin + 1024) / ITEM_CTAS - 1024 - 512;
+  const size_t item_fixed = (sizeof(ItemSmem<ITEM_BT>) + 15) & ~(size_t)15;
+  const int item_pool = (int)(item_dyn - item_fixed) - 16;
 
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
@@ -2070,6 +2125,10 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(cudaMemsetAsync(d_work, 0, 4 * sizeof(int), st));
   B200_CUDA(T.alloc(&d_bmslot, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_bmslot, 0xff, (size_t)std::max(m, 1) * sizeof(int), st));
+  int* d_rw = nullptr;            // range boundaries in bitmap words [RNG + 1] (ranges.cuh)
+  unsigned char* d_wr = nullptr;  // bitmap word -> range
+  unsigned* d_split = nullptr;    // [B.rows][RNG] offsets of the range boundaries inside a B row
+  int* d_rcnt = nullptr;          // [store_rows][RNG] output columns per range
   int* d_bsplit = nullptr;   // column-part boundaries inside every B row (k_bsplit)
   int* d_itemoff = nullptr;  // ticket offsets of the (row, part) slots of k_num_bitmap_part
   int* d_partcnt = nullptr;  // [m][PARTS_MAX] columns of the row per column part
@@ -2085,7 +2144,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   DevCSR Bs = B;
   int* d_bs_col = nullptr;
   double* d_bs_val = nullptr;
-  if (use_parts && nparts > 1 && !B.sorted_rows && B.nnz > 0) {
+  if (((use_parts && nparts > 1) || (want_ranges && nbig > 0)) && !B.sorted_rows && B.nnz > 0) {
     rc = sorted_copy_device(B, &d_bs_col, &d_bs_val);
     T.adopt(d_bs_col);
     T.adopt(d_bs_val);
@@ -2121,6 +2180,24 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     }
     store_rows = (int)std::min<size_t>((size_t)nbig, c.bm_store_words / (size_t)nw64);
     d_bmstore = store_rows ? c.bm_store : nullptr;
+    if (want_ranges && store_rows > 0 && Bs.nnz > 0) {
+      // static column ranges of equal column mass, their boundaries inside every B row
+      unsigned* d_hist = nullptr;
+      B200_CUDA(T.alloc(&d_hist, (size_t)nw64));
+      B200_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)nw64 * sizeof(unsigned), st));
+      B200_CUDA(T.alloc(&d_rw, (size_t)RNG + 1));
+      B200_CUDA(T.alloc(&d_wr, (size_t)nw64));
+      B200_CUDA(T.alloc(&d_split, (size_t)Bs.rows * RNG));
+      B200_CUDA(T.alloc(&d_rcnt, (size_t)store_rows * RNG));
+      const int hgrid = (int)std::min<long long>((Bs.nnz + 255) / 256, (long long)c.sm_count * 16);
+      k_col_hist<<<hgrid, 256, 0, st>>>(Bs.col, Bs.nnz, d_hist);
+      // a range is at most a quarter of the pool wide, so that any single range fits as a window
+      const int wcap = std::max(1, item_pool / 16 / 4);
+      k_make_ranges<<<1, 1024, 0, st>>>(d_hist, nw64, Bs.nnz, RNG, wcap, d_rw, d_wr);
+      k_range_split<<<(unsigned)(((long long)Bs.rows * 32 + 255) / 256), 256, 0, st>>>(
+          Bs.rowptr, Bs.col, Bs.rows, RNG, d_rw, d_split);
+      launches += 3;
+    }
     if (!sym_smem || !num_smem)
       B200_CUDA(T.alloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     tick(2 * SB_BITMAP);
@@ -2154,13 +2231,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       k_sym_bitmap<BT_BIG, true><<<big_grid, BT_BIG, walk_bytes + bm_bytes, st>>>(
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
           nw64, nullptr, d_bmstore, store_rows, d_bmslot, d_cnt, nparts, wpp, d_partcnt,
-          d_work + 0, l2m);
+          d_work + 0, l2m, d_wr, RNG, d_rcnt);
     } else {
       if ((rc = set_smem(k_sym_bitmap<BT_BIG, false>, walk_bytes))) return rc;
       k_sym_bitmap<BT_BIG, false><<<big_grid, BT_BIG, walk_bytes, st>>>(
           sb.d_list + sb.off[SB_BITMAP], nbig, row_lo, A.rowptr, A.col, B.rowptr, B.col, d_flops,
           nw64, d_gscr, d_bmstore, store_rows, d_bmslot, d_cnt, nparts, wpp, d_partcnt,
-          d_work + 0, l2m);
+          d_work + 0, l2m, nullptr, 0, nullptr);
     }
     tick(2 * SB_BITMAP + 1);
     ++launches;
@@ -2172,8 +2249,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   unsigned char* d_nbin = nullptr;
   B200_CUDA(T.alloc(&d_nbin, (size_t)m));
   if (m > 0) {
-    const long long light_p = getenv("B200_LIGHT_P") ? atoll(getenv("B200_LIGHT_P"))
-                                                     : 2560LL * std::max(1, nparts / 2);
+    const long long light_p = c.tun.light_p >= 0 ? c.tun.light_p : 2560LL * std::max(1, nparts / 2);
     k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p,
                                                 nparts > 2 ? light_p : 0, d_nbin);
     ++launches;
@@ -2303,7 +2379,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(T.alloc(&d_gscr, (size_t)c.sm_count * (bm_pref_bytes / 8)));
     const int* lst = nb.d_list + nb.off[NB_BITMAP];
     unsigned long long* d_prof = nullptr;
-    if (getenv("B200_PROF")) {
+    if (c.tun.prof) {
       B200_CUDA(T.alloc(&d_prof, 8));
       B200_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
     }
@@ -2319,8 +2395,70 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         ro, d_work + 1, d_prof, l2m);                                                           \
   } while (0)
     if (use_parts) {
+      // SpGEMM: straight into C; rMCL: the unpruned row into its arena slice, pruned in place by
+      // the epilogue kernel
+      int* out_col = mode == MODE_SPGEMM ? C->col : d_arena_col;
+      double* out_val = mode == MODE_SPGEMM ? C->val : d_arena_val;
+      // rows of the part kernel: all of them, or those the range planner could not take
+      const int* plist = lst;
+      int pcount = nbig_num;
+      if (d_rcnt) {
+        // ---- range items (ranges.cuh): plan, then one persistent launch
+        int *d_nitems = nullptr, *d_itoff = nullptr, *d_fb = nullptr, *d_fbcnt = nullptr;
+        B200_CUDA(T.alloc(&d_nitems, (size_t)nbig_num + 1));
+        B200_CUDA(T.alloc(&d_itoff, (size_t)nbig_num + 1));
+        B200_CUDA(T.alloc(&d_fb, (size_t)nbig_num));
+        B200_CUDA(T.alloc(&d_fbcnt, 1));
+        B200_CUDA(cudaMemsetAsync(d_nitems + nbig_num, 0, sizeof(int), st));
+        B200_CUDA(cudaMemsetAsync(d_fbcnt, 0, sizeof(int), st));
+        const int pgridp = (nbig_num + 255) / 256;
+        const int chunk_min = c.tun.deterministic ? 0 : c.tun.chunk_min;
+        const int short_mode = c.tun.no_tag ? ITEM_RED : ITEM_TAG;
+        k_plan_items<<<pgridp, 256, 0, st>>>(lst, nbig_num, d_bmslot, d_rcnt, d_rw, RNG, item_pool,
+                                             chunk_min, short_mode, nw64, d_flops, A.rowptr, row_lo,
+                                             d_urp, d_nitems, nullptr, nullptr, d_fb, d_fbcnt);
+        {
+          void* tmp = nullptr;
+          size_t tb = 0;
+          cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nitems, d_itoff, nbig_num + 1, st);
+          B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, st));
+          cub::DeviceScan::ExclusiveSum(tmp, tb, d_nitems, d_itoff, nbig_num + 1, st);
+          cudaFreeAsync(tmp, st);
+        }
+        int h_items = 0, h_fb = 0;
+        B200_CUDA(d2h_small(&h_items, d_itoff + nbig_num, sizeof(int), st));
+        B200_CUDA(d2h_small(&h_fb, d_fbcnt, sizeof(int), st));
+        B200_CUDA(sync_fetch(st));
+        launches += 2;
+        if (h_items > 0) {
+          RangeItem* d_items = nullptr;
+          B200_CUDA(T.alloc(&d_items, (size_t)h_items));
+          k_plan_items<<<pgridp, 256, 0, st>>>(lst, nbig_num, d_bmslot, d_rcnt, d_rw, RNG, item_pool,
+                                               chunk_min, short_mode, nw64, d_flops, A.rowptr, row_lo,
+                                               d_urp, d_nitems, d_itoff, d_items, d_fb, d_fbcnt);
+          if ((rc = set_smem(k_num_items<ITEM_BT, ITEM_CTAS>, item_dyn))) return rc;
+          const int igrid = std::min(h_items, ITEM_CTAS * c.sm_count);
+          k_num_items<ITEM_BT, ITEM_CTAS><<<igrid, ITEM_BT, item_dyn, st>>>(
+              d_items, h_items, RNG, A.col, A.val, Bs.rowptr, Bs.col, Bs.val, d_split, d_bmstore,
+              out_col, out_val, l2m, d_prof);
+          launches += 2;
+          if (d_prof) {
+            unsigned long long h[8];
+            B200_CUDA(d2h_small(h, d_prof, sizeof h, st));
+            B200_CUDA(sync_fetch(st));
+            B200_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
+            fprintf(stderr, "[b200 prof] k_num_items: %d items (%d fallback rows), Mcycles/CTA: window %.2f zero %.2f "
+                    "table %.2f walk %.2f flush %.2f | walk: wait+rank %.2f rounds %.2f issue(1/3) %.2f (grid %d)\n", h_items, h_fb, h[0] / 1e6 / igrid,
+                    0.0, h[1] / 1e6 / igrid, h[2] / 1e6 / igrid, h[3] / 1e6 / igrid, h[4] / 1e6 / igrid, h[5] / 1e6 / igrid, h[6] / 1e6 / igrid, igrid);
+          }
+        }
+        range_items = h_items;
+        plist = d_fb;
+        pcount = h_fb;
+      }
+      if (pcount > 0) {
       // team sizes -> ticket offsets of the (row, part) slots
-      const int nslots = nbig_num * nparts;
+      const int nslots = pcount * nparts;
       int* d_tsize = nullptr;
       int* d_ready = nullptr;
       B200_CUDA(T.alloc(&d_tsize, (size_t)nslots + 1));
@@ -2336,14 +2474,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
           ++launches;
         }
       }
-      const long long team_products = getenv("B200_TEAM_P") ? atoll(getenv("B200_TEAM_P")) : 98304;
       // a team must fit, with room to spare, among the CTAs that are resident at once (its
       // members wait for each other): at most half of one CTA per SM
       const int team_cap = std::max(1, c.sm_count / 2);
-      const int team_max =
-          std::min(team_cap, getenv("B200_TEAM_MAX") ? atoi(getenv("B200_TEAM_MAX")) : 64);
-      k_team_sizes<<<(nslots + 255) / 256, 256, 0, st>>>(lst, nbig_num, nparts, d_flops, d_partcnt,
-                                                         team_products, team_max, d_tsize);
+      const int team_max = std::min(team_cap, c.tun.team_max);
+      k_team_sizes<<<(nslots + 255) / 256, 256, 0, st>>>(plist, pcount, nparts, d_flops, d_partcnt,
+                                                         c.tun.team_products, team_max, d_tsize);
       {
         void* tmp = nullptr;
         size_t tb = 0;
@@ -2365,16 +2501,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   do {                                                                                          \
     if ((rc = set_smem(k_num_bitmap_part<BTP, MINB>, part_smem))) return rc;                    \
     k_num_bitmap_part<BTP, MINB><<<pgrid, BTP, part_smem, st>>>(                                \
-        lst, nbig_num, nparts, wpp, row_lo, A.rowptr, A.col, A.val, Bs.rowptr, Bs.col, Bs.val,  \
+        plist, pcount, nparts, wpp, row_lo, A.rowptr, A.col, A.val, Bs.rowptr, Bs.col, Bs.val,  \
         nw64, d_bmstore, d_bmslot, d_partcnt, d_urp, out_col, out_val, d_itemoff,               \
         d_ticket_slot, d_ready, d_bsplit, B.rows, d_work + 1, l2m);                             \
   } while (0)
-      // SpGEMM: straight into C; rMCL: the unpruned row into its arena slice, pruned in place by
-      // the epilogue kernel
-      int* out_col = mode == MODE_SPGEMM ? C->col : d_arena_col;
-      double* out_val = mode == MODE_SPGEMM ? C->val : d_arena_val;
       if (parts4) LAUNCH_PART(256, 4); else LAUNCH_PART(512, 2);
 #undef LAUNCH_PART
+      }
       if (mode == MODE_RMCL) {
         const int egrid = std::min(nbig_num, c.sm_count * 8);
         k_rmcl_epilogue_rows<256><<<egrid, 256, 0, st>>>(lst, nbig_num, d_urp, ro, d_work + 2);
@@ -2476,6 +2609,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->launches = launches;
     stats->part_kernel = use_parts ? 1 : 0;
     stats->part_count = nparts;
+    stats->range_items = range_items;
+    stats->ranges = range_items ? RNG : 0;
     for (int b = 0; b < 16; ++b) {
       stats->bins_rows[b] = nb.cnt[b];
       stats->sym_bin_rows[b] = sb.cnt[b];

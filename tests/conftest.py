@@ -34,3 +34,16 @@ def gpu(smf):
     """Initialised GPU context; the C-ABI fails loudly when there is no device."""
     smf.init(0)
     return smf
+
+
+@pytest.fixture
+def b200_options(gpu, monkeypatch):
+    """Set B200_* developer switches for one test: the library reads them once (b200_init), so
+    they are re-read after every change and again after the test's environment is restored."""
+    def set_options(**kw):
+        for k, v in kw.items():
+            monkeypatch.setenv(k, str(v))
+        gpu.reload_options()
+    yield set_options
+    monkeypatch.undo()
+    gpu.reload_options()

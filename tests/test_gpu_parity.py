@@ -139,17 +139,72 @@ def test_rmcl_to_convergence(gpu):
 
 
 @pytest.mark.parametrize("name,make", SYNTH)
-def test_wide_fallback_paths(gpu, name, make, monkeypatch):
+def test_wide_fallback_paths(gpu, name, make, b200_options):
     """B200_FORCE_WIDE=1 makes the library treat B as too wide for a shared-memory bitmap: the
     optimistic / full-size warp tables (with the device-side overflow retry) and the HBM-bitmap
     kernels then handle these inputs.  Same parity bar."""
-    monkeypatch.setenv("B200_FORCE_WIDE", "1")
+    b200_options(B200_FORCE_WIDE=1)
     A = make(gpu)
     ol.assert_same(gpu_spgemm(gpu, A, A), want_spgemm(A, A), TOL, name + " wide")
     want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
     step = A.staticOmpRmclOneStep(A)
     step.makeOrdered()
     ol.assert_same(M_of(step), want1, TOL, name + " wide rMCL step")
+
+
+HEAVY = [
+    ("rmat12_dir", lambda s: s.synth_rmat(12, 16, 12345, False)),
+    ("rmat13_sym", lambda s: s.synth_rmat(13, 16, 3, True)),           # hub rows with > 10^3 A entries
+    ("planted_dense", lambda s: s.synth_planted(3000, 3, 60, 4, 7)),   # ~1000-column rows, ~16 K products
+]
+# the numeric pass of the heavy rows: on-chip range items (default: mode chosen per item), every
+# item forced to commit in A-entry order / by tag arbitration / with global RED accumulators,
+# few wide / many narrow ranges, and the part kernel alone
+HEAVY_MODES = [
+    ("default", {}),                                   # part kernel: global fp64 RED
+    ("on_chip", {"B200_ON_CHIP": 1}),                  # range items, mode chosen per item
+    ("all_ordered", {"B200_DETERMINISTIC": 1}),
+    ("all_tag", {"B200_ON_CHIP": 1, "B200_CHUNK_MIN": 1000000000}),
+    ("all_red", {"B200_ON_CHIP": 1, "B200_CHUNK_MIN": 1000000000, "B200_NO_TAG": 1}),
+    ("ranges4_tag", {"B200_ON_CHIP": 1, "B200_RANGES": 4, "B200_CHUNK_MIN": 1000000000}),
+    ("ranges7_ordered", {"B200_ON_CHIP": 1, "B200_RANGES": 7, "B200_CHUNK_MIN": 0}),
+]
+
+
+@pytest.mark.parametrize("mode,opts", HEAVY_MODES)
+@pytest.mark.parametrize("name,make", HEAVY)
+def test_heavy_row_paths(gpu, name, make, mode, opts, b200_options):
+    """Rows of more than 256 output columns: every way the numeric pass can take them gives the
+    reference's structure exactly and its values within 1e-12; the same for one rMCL step."""
+    b200_options(**opts)
+    A = make(gpu)
+    dA = A.toGpuCSR()
+    dC, st = gpu.gpuSpMMWrapper(dA, dA, want_stats=True)
+    got = M_of(dC.toCpuCSR())
+    dC.deviceDispose()
+    dA.deviceDispose()
+    assert st["bins_rows"][5] > 0, "test input must have rows in the bitmap bin"
+    assert (st["range_items"] > 0) == (mode != "default"), st["range_items"]
+    ol.assert_same(got, want_spgemm(A, A), TOL, name + " " + mode)
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+    step = A.staticOmpRmclOneStep(A)
+    step.makeOrdered()
+    ol.assert_same(M_of(step), want1, TOL, name + " " + mode + " rMCL step")
+
+
+@pytest.mark.parametrize("name,make", HEAVY)
+def test_on_chip_items_are_bit_identical(gpu, name, make, b200_options):
+    """An ordered on-chip item commits the B-row segments in A-entry order with separately rounded
+    multiply and add (indexProcessCRowI's order): with B200_DETERMINISTIC every item runs that
+    way and the whole product equals the reference's bit for bit — heavy rows included — and is
+    the same on every run."""
+    b200_options(B200_DETERMINISTIC=1)
+    A = make(gpu)
+    got, want = gpu_spgemm(gpu, A, A), want_spgemm(A, A)
+    assert np.array_equal(got.I, want.I) and np.array_equal(got.J, want.J)
+    assert np.array_equal(got.V.view(np.int64), want.V.view(np.int64))
+    again = gpu_spgemm(gpu, A, A)
+    assert np.array_equal(again.V.view(np.int64), got.V.view(np.int64))
 
 
 def test_sharded_loop_single_rank(gpu):
