@@ -66,6 +66,7 @@ typedef struct b200_stats {
   int part_count;      /* column parts it used */
   int range_items;     /* work items of the on-chip numeric pass (k_num_items); 0: not used */
   int ranges;          /* static column ranges it planned with */
+  int row_tiles;       /* rMCL step: row tiles it ran through the bounded arena (0 or 1: one pass) */
 } b200_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -212,6 +213,13 @@ int b200_comm_destroy(void);
  * on every rank (the old handle is freed). */
 int b200_rmcl_iter_sharded(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* Mt_io,
                            int* iters_done, double* chaos_hist, double* ms_per_iter);
+/* The same loop; counts_per_iter (may be NULL; room for 4 * maxIter values) receives per
+ * iteration {intermediate products of the whole step, nnz of the new Mt, its unpruned nnz summed
+ * over the ranks, most row tiles any rank ran the step in} — what a harness needs for the
+ * roofline of an iteration. */
+int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* Mt_io,
+                                 int* iters_done, double* chaos_hist, double* ms_per_iter,
+                                 long long* counts_per_iter);
 
 /* ---- synthetic inputs (harness) ---------------------------------------- *
  * All return a malloc()'d int CSR with rmclInit semantics (nlibs/qrmcl.cc:126-134): self loop

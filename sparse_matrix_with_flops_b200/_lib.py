@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("part_count", C.c_int),
         ("range_items", C.c_int),
         ("ranges", C.c_int),
+        ("row_tiles", C.c_int),
     ]
 
     def as_dict(self):
@@ -103,6 +104,8 @@ SIGNATURES = {
     "b200_comm_destroy": (C.c_int, []),
     "b200_rmcl_iter_sharded": (C.c_int, [C.c_int, C.c_double, csr_t, C.POINTER(csr_t), c_int_p,
                                          c_double_p, c_double_p]),
+    "b200_rmcl_iter_sharded_stats": (C.c_int, [C.c_int, C.c_double, csr_t, C.POINTER(csr_t), c_int_p,
+                                               c_double_p, c_double_p, c_ll_p]),
     "b200_synth_rmat": (C.c_int, [C.c_int, C.c_int, C.c_ulonglong, C.c_int, c_int_p,
                                   C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p), c_ll_p]),
     "b200_synth_stencil27": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(c_int_p),

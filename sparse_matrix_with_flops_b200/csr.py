@@ -281,7 +281,7 @@ def comm_destroy():
     check(_lib.load().b200_comm_destroy())
 
 
-def gpuRmclIterSharded(maxIter, dMgt, dMt, eps=0.0):
+def gpuRmclIterSharded(maxIter, dMgt, dMt, eps=0.0, want_counts=False):
     """b200_rmcl_iter_sharded: every rank holds Mgt and Mt (device); rank r computes the r-th
     flops-balanced row block each iteration, the pruned blocks are all-gathered and chaos is
     max-reduced.  dMt is replaced by the final Mt (sorted rows).  Returns
@@ -292,9 +292,14 @@ def gpuRmclIterSharded(maxIter, dMgt, dMt, eps=0.0):
     ms = np.zeros(max(1, maxIter), dtype=np.float64)
     if not isinstance(dMt.handle, csr_t):
         dMt.handle = csr_t(dMt.handle)
-    check(lib.b200_rmcl_iter_sharded(int(maxIter), float(eps), dMgt.handle, C.byref(dMt.handle),
-                                     C.byref(iters), _dp(hist), _dp(ms)))
-    return iters.value, hist[:iters.value].copy(), ms[:iters.value].copy()
+    counts = np.zeros(4 * max(1, maxIter), dtype=np.int64)
+    check(lib.b200_rmcl_iter_sharded_stats(int(maxIter), float(eps), dMgt.handle, C.byref(dMt.handle),
+                                           C.byref(iters), _dp(hist), _dp(ms),
+                                           counts.ctypes.data_as(_lib.c_ll_p) if want_counts else None))
+    out = (iters.value, hist[:iters.value].copy(), ms[:iters.value].copy())
+    if want_counts:   # per iteration: products, nnz(new Mt), unpruned nnz, row tiles
+        out += (counts.reshape(-1, 4)[:iters.value].copy(),)
+    return out
 
 
 def rmclInit(rows_idx, cols_idx, n):

@@ -765,7 +765,7 @@ int b200_rmcl_step_device_rows(b200_csr_t Mgt, b200_csr_t Mt, int row_lo, int ro
   if (!newMt) { set_error("null output handle"); return B200_ERR_BAD_ARG; }
   b200_csr* h = new b200_csr();
   double ch = 0.0;
-  rc = run_pipeline(Mgt->d, Mt->d, row_lo, row_hi, MODE_RMCL, &h->d, &ch, stats);
+  rc = rmcl_step_device(Mgt->d, Mt->d, row_lo, row_hi, &h->d, &ch, stats);
   if (rc) { release(h->d); delete h; return rc; }
   if (chaos) *chaos = ch;
   *newMt = h;
@@ -874,7 +874,8 @@ static int host_mul(Mode mode, const int* IA, const int* JA, const double* A, in
   if (rc) return rc;
   rc = upload(IB, JB, B, k, n, nnzB, &dB);
   if (rc) { release(dA); return rc; }
-  rc = run_pipeline(dA, dB, 0, m, mode, &dC, chaos, nullptr);
+  rc = mode == MODE_RMCL ? rmcl_step_device(dA, dB, 0, m, &dC, chaos, nullptr)
+                         : run_pipeline(dA, dB, 0, m, mode, &dC, chaos, nullptr);
   if (!rc) {
     if (dC.nnz > INT_MAX) {
       set_error("nnz(C) exceeds INT_MAX: use the row-block device API");
@@ -939,7 +940,7 @@ int b200_rmcl_iter(int maxIter, double eps, const int* IG, const int* JG, const 
   for (; it < maxIter; ++it) {
     DevCSR dN;
     double ch = 0.0;
-    rc = run_pipeline(dG, dT, 0, n, MODE_RMCL, &dN, &ch, nullptr);
+    rc = rmcl_step_device(dG, dT, 0, n, &dN, &ch, nullptr);
     if (rc) { release(dN); break; }
     release(dT);  // Mt.dispose(); Mt = newMt  (nlibs/qrmcl.cc:72-73)
     dT = dN;

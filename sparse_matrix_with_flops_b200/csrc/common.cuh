@@ -48,6 +48,7 @@ struct Tunables {
   long long light_p = -1;
   long long team_products = 98304;  // B200_TEAM_P, B200_TEAM_MAX: team sizing of the part kernel
   int team_max = 64;
+  long long arena_entries = 0;  // B200_ARENA_ENTRIES: products per row tile of an rMCL step (0: from free memory)
   int ranges = 64;      // B200_RANGES: static column ranges of the on-chip numeric pass (2..64)
   int chunk_min = 96;   // B200_CHUNK_MIN: items whose expected B-row segments are shorter do not
                         // commit in A-entry order (a barrier per segment) but by tag arbitration
@@ -85,6 +86,7 @@ struct Ctx {
   int* arena_col = nullptr;
   double* arena_val = nullptr;
   size_t arena_cap = 0;
+  long long arena_budget = 0;  // entries a row tile of an rMCL step may hold (tiles.cu); 0: not sized yet
   // small read-backs (row totals, bin counts): a kernel writes them into mapped pinned memory
   // instead of a cudaMemcpy, because the device-to-host copy engine may be busy for 100+ ms with
   // a streamed download (profiles/r1_stream_blocks_rmat20.txt)
@@ -168,8 +170,19 @@ int coo_build_device(const int* d_row, const int* d_col, const double* d_val, lo
                      int cols, int flags, DevCSR* out);
 
 // Core pipeline (spgemm.cu): C = A[row_lo:row_hi) x B, or the fused rMCL step.
+// `Bsorted`: a column-sorted copy of B the caller already has (used when the bitmap kernels need
+// one and B's rows are unsorted; nullptr: made on demand, per call).
 int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode,
-                 DevCSR* C, double* chaos, b200_stats* stats);
+                 DevCSR* C, double* chaos, b200_stats* stats, const DevCSR* Bsorted = nullptr);
+// One rMCL step newMt[row_lo:row_hi) through a bounded arena (tiles.cu): the entry point every
+// rMCL caller uses.
+int rmcl_step_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, DevCSR* C,
+                     double* chaos, b200_stats* stats);
+// (col, val) of `d` sorted by column inside every row; shares d's row offsets (spgemm.cu)
+int sorted_copy_of(const DevCSR& d, DevCSR* out);
+// concatenation of row blocks (tiles.cu); arrayEqualPartition64 on a device prefix (tiles.cu)
+int concat_rows_device(const std::vector<DevCSR>& blocks, int cols, DevCSR* out);
+int equal_partition_device(const int64_t* d_prefix, int n, int nparts, int* h_ends);
 
 // CSR::makeOrdered on the device (spgemm.cu)
 int sort_rows_device(DevCSR* d);

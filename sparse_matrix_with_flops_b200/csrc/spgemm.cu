@@ -1791,6 +1791,7 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_TEAM_P")) t->team_products = std::max(1LL, atoll(e));
   if (const char* e = getenv("B200_TEAM_MAX")) t->team_max = std::max(1, atoi(e));
   if (const char* e = getenv("B200_RANGES")) t->ranges = atoi(e);
+  if (const char* e = getenv("B200_ARENA_ENTRIES")) t->arena_entries = atoll(e);
   if (const char* e = getenv("B200_CHUNK_MIN")) t->chunk_min = atoi(e);
   t->no_tag = flag("B200_NO_TAG");
   t->deterministic = flag("B200_DETERMINISTIC");
@@ -1946,8 +1947,20 @@ static cudaError_t malloc_with_trim(void** p, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
+int sorted_copy_of(const DevCSR& d, DevCSR* out) {
+  *out = d;
+  int* col2 = nullptr;
+  double* val2 = nullptr;
+  const int rc = sorted_copy_device(d, &col2, &val2);
+  if (rc) { dfree(col2); dfree(val2); return rc; }
+  out->col = col2;
+  out->val = val2;
+  out->sorted_rows = true;
+  return B200_OK;
+}
+
 int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode mode, DevCSR* C,
-                 double* chaos, b200_stats* stats) {
+                 double* chaos, b200_stats* stats, const DevCSR* Bsorted) {
   Ctx& c = ctx();
   cudaStream_t st = c.stream;
   const int m = row_hi - row_lo;
@@ -2144,7 +2157,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   DevCSR Bs = B;
   int* d_bs_col = nullptr;
   double* d_bs_val = nullptr;
-  if (((use_parts && nparts > 1) || (want_ranges && nbig > 0)) && !B.sorted_rows && B.nnz > 0) {
+  if (((use_parts && nparts > 1) || (want_ranges && nbig > 0)) && !B.sorted_rows && B.nnz > 0 && Bsorted) {
+    Bs = *Bsorted;
+  } else if (((use_parts && nparts > 1) || (want_ranges && nbig > 0)) && !B.sorted_rows && B.nnz > 0) {
     rc = sorted_copy_device(B, &d_bs_col, &d_bs_val);
     T.adopt(d_bs_col);
     T.adopt(d_bs_val);

@@ -207,6 +207,63 @@ def test_on_chip_items_are_bit_identical(gpu, name, make, b200_options):
     assert np.array_equal(again.V.view(np.int64), got.V.view(np.int64))
 
 
+@pytest.mark.parametrize("name,make", [SYNTH[0], SYNTH[2], SYNTH[5], HEAVY[2]])
+def test_rmcl_through_a_bounded_arena(gpu, name, make, b200_options):
+    """The rMCL step never needs the unpruned product of the whole step in memory
+    (static_omp_csr_kernel.cc:241-242 allocates it): with a small arena the rows run as
+    consecutive tiles, each pruned on its own.  Same iterates as one pass and as the checker."""
+    A = make(gpu)
+    dG = A.toGpuCSR()
+    one, ch1, st1 = gpu.gpuRmclOneStep(dG, dG, want_stats=True)
+    assert st1["row_tiles"] <= 1
+    b200_options(B200_ARENA_ENTRIES=max(1000, st1["products"] // 7))
+    til, ch2, st2 = gpu.gpuRmclOneStep(dG, dG, want_stats=True)
+    assert st2["row_tiles"] >= 5, st2["row_tiles"]
+    assert st2["products"] == st1["products"] and st2["nnz_unpruned"] == st1["nnz_unpruned"]
+    a, b = one.toCpuCSR(), til.toCpuCSR()
+    one.deviceDispose(); til.deviceDispose(); dG.deviceDispose()
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+    assert np.array_equal(a.rowPtr, b.rowPtr)
+    ol.assert_same(M_of(b.makeOrdered()), want1, TOL, name + " tiled step")
+    assert abs(ch2 - ol.o_chaos(want1)) <= 1e-12 and abs(ch1 - ch2) <= 1e-12
+    # the loop, every iteration tiled
+    want, it_w, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 6)
+    ol.o_make_ordered(want)
+    Mt, iters, hist = gpu.gpuRmclIter(6, A, A)
+    ol.assert_same(M_of(Mt), want, TOL, name + " tiled loop")
+    assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
+
+
+def test_sharded_loop_two_ranks_nccl():
+    """b200_rmcl_iter_sharded on 2 GPUs (NCCL all-gather of the pruned row blocks + chaos) against
+    the checker, one process per GPU.  Needs two devices: skipped on a single-GPU box."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for kind, size, iters in (("planted", "20000", "6"), ("rmat", "12", "5")):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29731",
+                              os.path.join(root, "tools", "run_sharded_rmcl.py"), kind, size, iters],
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "parity with the checker: OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_device_partition_matches_host_partition(gpu):
+    """The sharded loop finds its cut points on the device; same arithmetic as
+    arrayEqualPartition64 (util.cc:123-135): a 1-rank and the tiled path exercise it; here the
+    flops prefix from the device gives the same cuts through the host routine for 1..9 parts."""
+    A = gpu.synth_rmat(12, 16, 5, True)
+    dA = A.toGpuCSR()
+    prefix = gpu.flops_prefix(dA, dA)
+    dA.deviceDispose()
+    assert np.array_equal(prefix, ol.o_flops_prefix(M_of(A), M_of(A)))
+    for parts in range(1, 10):
+        ends = gpu.arrayEqualPartition64(prefix, parts)
+        assert np.array_equal(ends, ol.o_equal_partition64(prefix, parts))
+
+
 def test_sharded_loop_single_rank(gpu):
     """b200_rmcl_iter_sharded with one rank (no collective): same iterates as the reference loop.
     The 2-rank NCCL path is exercised by tools/run_sharded_rmcl.py under torchrun."""
