@@ -50,7 +50,7 @@ import time
 _world = int(os.environ.get("WORLD_SIZE", "1"))
 _is_ref = "reference" in sys.argv
 os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // (1 if _is_ref else _world)))
-os.environ.setdefault("OMP_PROC_BIND", "false")
+os.environ.setdefault("OMP_PROC_BIND", "close")   # BASELINE.md §3 / SURVEY.md §8d timing protocol
 
 import numpy as np
 
@@ -75,10 +75,17 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rmat20",
-                    help="rmat<scale> (directed, edge factor 16) | stencil<g> (g^3 27-point)")
+                    help="A*A: rmat<scale> (directed, edge factor 16) | stencil<g> (g^3 27-point) | "
+                         "planted<n>c<clusters>;  rMCL loop: rmcl-rmat<scale>[e<edge factor>] "
+                         "(symmetrised) | rmcl-planted<n>c<clusters>")
+    ap.add_argument("--rmcl-iters", type=int, default=5,
+                    help="iterations of one rMCL loop (the reference's default maxIters, process_args.h:28)")
+    ap.add_argument("--rmcl-leg", default="rmcl-rmat20",
+                    help="rMCL workload measured next to an A*A headline and reported under \"rmcl\" "
+                         "(BASELINE metric: SpGEMM GFLOP/s + rMCL iter/s); 'none' skips it")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="development: skip the CPU baseline leg")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--row-charge", type=int, default=32768,
                     help="products-equivalent fixed cost of a heavy row in the N>1 row partition")
     return ap.parse_args()
@@ -93,9 +100,39 @@ def make_workload(smf, name):
         g = int(name[7:])
         A = smf.synth_stencil27(g, g, g)
         desc = "C=A*A, 27-point stencil on a %d^3 grid" % g
+    elif name.startswith("planted"):
+        n, k = (int(x) for x in name[7:].split("c"))
+        A = smf.synth_planted(n, k, 16, 2, 12345)
+        desc = "C=A*A, planted partition %d vertices %d blocks (16 intra + 2 inter draws per vertex)" % (n, k)
     else:
         raise SystemExit("unknown workload " + name)
     return A, desc
+
+
+def make_rmcl_workload(smf, name):
+    """rMCL inputs: Mgt = Mt0 = rmclInit of a symmetrised, de-duplicated graph."""
+    body = name[len("rmcl-"):]
+    if body.startswith("rmat"):
+        parts = body[4:].split("e")
+        scale, ef = int(parts[0]), (int(parts[1]) if len(parts) > 1 else 16)
+        A = smf.synth_rmat(scale, ef, 12345, True)
+        desc = "rMCL loop on R-MAT scale %d edge factor %d symmetrised, seed 12345" % (scale, ef)
+        small = "rmcl-rmat%de%d" % (min(scale, 15), ef)
+    elif body.startswith("planted"):
+        n, k = (int(x) for x in body[7:].split("c"))
+        A = smf.synth_planted(n, k, 16, 2, 12345)
+        desc = "rMCL loop on planted partition %d vertices %d blocks" % (n, k)
+        ns = min(n, 100000)
+        small = "rmcl-planted%dc%d" % (ns, max(1, k * ns // n))
+    else:
+        raise SystemExit("unknown rMCL workload " + name)
+    return A, desc, small
+
+
+def rmcl_iter_bytes(n, nnzG, products, nnz_new):
+    """ALGORITHMIC bytes of one fused rMCL iteration: A = Mgt rows, gathered
+    B = Mt rows (12 B per product + the row-pointer pair per A entry), C = the PRUNED new Mt."""
+    return 12 * nnzG + 4 * (n + 1) + 12 * products + 8 * nnzG + 12 * nnz_new + 4 * (n + 1)
 
 
 def host_flops_prefix(A):
@@ -254,6 +291,226 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+
+# ---- rMCL loop (BASELINE metric, second half: rMCL iterations / second) -----------------------
+
+RMCL_METRIC = "rmcl_iters_per_s"
+RMCL_UNIT = "iter/s"
+
+
+class quiet_stdout:
+    """The reference's loop prints a line per iteration (nlibs/qrmcl.cc:66-70) on the C stdout;
+    the bench line must stay the only thing on ours."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:  # noqa: BLE001
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
+def rmcl_cpu_baseline(smf, small_name, iters, full_products_per_iter):
+    """The reference's own loop (mtRmclIter with static_omp_CSR_RMCL_OneStep, nlibs/qrmcl.cc:8-84
+    through oracle/_ref; the checker's port when the reference library is absent) on a smaller
+    graph of the same family — the full one does not fit the reference's `int` CSR — timed on
+    the host cores.  Its products / second, divided by the full workload's products per
+    iteration, is the CPU's equivalent iterations / second on the full workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    As, desc_s, _ = make_rmcl_workload(smf, small_name)
+    M = ol.from_csr(As)
+    # products of the sample loop, from the checker's flops analysis of every iterate
+    kind = "reference" if os.path.exists(ol.REF_SO) else "port"
+    if kind == "reference":
+        cores = ol.ref().ref_num_threads()
+        with quiet_stdout():
+            ol.r_rmcl_iter(M, M, 1)                   # warm-up (thread scratch, page faults)
+            ms = ol.r_rmcl_iter(M, M, iters).ms
+    else:
+        cores = 1
+        t0 = time.perf_counter()
+        ol.o_rmcl_iter(M, M, iters)
+        ms = (time.perf_counter() - t0) * 1e3
+    T, prods = M, 0
+    for _ in range(iters):
+        prods += int(ol.o_flops_prefix(M, T)[-1])
+        T = ol.o_rmcl_onestep(M, T)
+    pps = prods / (ms * 1e-3)
+    return {"value": pps / full_products_per_iter, "unit": RMCL_UNIT, "cores": cores, "kind": kind,
+            "sample": "%s: %d iterations, %d products in %.1f ms (%.3g products/s = %.3f iter/s there); value = "
+                      "that rate / the full workload's %.4g products per iteration" % (
+                          desc_s, iters, prods, ms, pps, iters / (ms * 1e-3), full_products_per_iter),
+            "sample_iters_per_s": iters / (ms * 1e-3), "products_per_s": pps, "ms": ms}
+
+
+def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
+    """K rMCL loops of --rmcl-iters iterations each (a step = one loop from Mt0 = Mgt) through
+    b200_rmcl_iter_sharded: at N > 1 every iteration cuts the rows into N flops-balanced
+    blocks, all-gathers the pruned blocks over NCCL and max-reduces chaos."""
+    import torch
+    import torch.distributed as dist
+    smf, lib, stream, barrier, rank, world = (env[k] for k in ("smf", "lib", "stream", "barrier", "rank", "world"))
+    A, desc, small = make_rmcl_workload(smf, name)
+    iters = args.rmcl_iters
+    if world > 1 and not env.get("comm"):
+        uid = [smf.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        with quiet_stdout():
+            smf.comm_init(rank, world, uid[0])
+        env["comm"] = True
+    dG = A.toGpuCSR()
+
+    def loop(dT):
+        return smf.gpuRmclIterSharded(iters, dG, dT, want_counts=True)
+
+    for _ in range(warmup):
+        dT = A.toGpuCSR()
+        loop(dT)
+        dT.deviceDispose()
+    dTs = [A.toGpuCSR() for _ in range(steps)]     # Mt0 of every timed loop: resident before the clock starts
+    barrier()
+    sampler = ClockSampler(env["local"]) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    for dT in dTs:
+        done, hist, ms_it, counts = loop(dT)
+        launches += int(counts[:, 4].sum())
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    nnz_final = dTs[-1].info()[2]
+    for dT in dTs:
+        dT.deviceDispose()
+    t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(tmax[0]), int(t[1])
+    ms_loop = ms_total / steps
+    value = done / (ms_loop * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    bytes_it = [rmcl_iter_bytes(A.rows, A.nnz, int(counts[k, 0]), int(counts[k, 1])) for k in range(done)]
+    achieved = sum(bytes_it) / (ms_loop * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "one rMCL loop (every kernel of its %d fused iterations)" % done,
+                "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                "traffic": None, "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
+                "loop_algorithmic_bytes": int(sum(bytes_it)),
+                "per_iteration": {"ms": [round(float(x), 3) for x in ms_it],
+                                  "products": [int(x) for x in counts[:, 0]],
+                                  "nnz_new_Mt": [int(x) for x in counts[:, 1]],
+                                  "nnz_unpruned": [int(x) for x in counts[:, 2]],
+                                  "row_tiles": [int(x) for x in counts[:, 3]],
+                                  "chaos": [float(x) for x in hist]}}
+    # ---- e2e: host CSR in, host CSR out, every copy inside the clock
+    e2e = None
+    if want_e2e:
+        def one():
+            if world == 1:
+                Mt, it, _ = smf.gpuRmclIter(iters, A, A)
+                return Mt.nnz
+            g, tt = A.toGpuCSR(), A.toGpuCSR()
+            smf.gpuRmclIterSharded(iters, g, tt)
+            Mt = tt.toCpuCSR()
+            g.deviceDispose(); tt.deviceDispose()
+            return Mt.nnz
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            nz = one()
+        barrier()
+        sec = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt[0])
+        per = 4 * (A.rows + 1) + 12 * A.nnz
+        e2e = {"value": iters / sec, "unit": RMCL_UNIT, "h2d_bytes_per_step": 2 * per * world,
+               "d2h_bytes_per_step": (4 * (A.rows + 1) + 12 * nz) * world, "ms_per_step": sec * 1e3,
+               "steps": args.e2e_steps, "warmup": 1,
+               "api": ("b200_rmcl_iter (host int CSR of Mgt and Mt in, malloc'd host int CSR of the final Mt out)"
+                       if world == 1 else
+                       "per rank: b200_csr_upload x2 + b200_rmcl_iter_sharded + b200_csr_download") +
+                      ", wall clock incl. H2D + D2H"}
+    cpu = None
+    if want_cpu and rank == 0 and world == 1:
+        cpu = rmcl_cpu_baseline(smf, small, iters, float(np.mean(counts[:, 0])))
+    dG.deviceDispose()
+    return {"metric": RMCL_METRIC, "value": value, "unit": RMCL_UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_loop, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "rows": A.rows, "nnz_Mgt": A.nnz, "iterations_per_loop": done,
+                       "nnz_final": int(nnz_final),
+                       "partition": "flops-balanced contiguous row blocks of Mgt, recomputed every iteration (arrayEqualPartition64)",
+                       "collectives": ("none (1 rank)" if world == 1 else
+                                       "per iteration, in the library's own NCCL communicator (%d ranks): ncclAllGather of "
+                                       "{block nnz, status, chaos} + grouped ncclBroadcast of the pruned row blocks" % world),
+                       "l2": "no flush: every iteration reads the previous iteration's output; operands exceed L2 from scale 18 on"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+
+
+def run_reference_rmcl(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import sparse_matrix_with_flops_b200 as smf  # generator library only (host code)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    A, desc, small = make_rmcl_workload(smf, args.workload)
+    As, desc_s, _ = make_rmcl_workload(smf, small)
+    M = ol.from_csr(As)
+    kind = "reference" if os.path.exists(ol.REF_SO) else "port"
+    iters = args.rmcl_iters
+
+    def one():
+        if kind == "reference":
+            with quiet_stdout():
+                return ol.r_rmcl_iter(M, M, iters).ms
+        t0 = time.perf_counter()
+        ol.o_rmcl_iter(M, M, iters)
+        return (time.perf_counter() - t0) * 1e3
+    for _ in range(max(1, min(args.warmup, 1))):
+        one()
+    ms = float(np.mean([one() for _ in range(max(1, min(args.steps, 3)))]))
+    # rate-vs-rate: the sample's products / second against the full workload's products per iteration
+    T, prods = M, 0
+    for _ in range(iters):
+        prods += int(ol.o_flops_prefix(M, T)[-1])
+        T = ol.o_rmcl_onestep(M, T)
+    Mf, Tf, full = ol.from_csr(A), None, []
+    full_p0 = int(ol.o_flops_prefix(Mf, Mf)[-1])   # iteration 0 of the full workload (later iterates need the GPU)
+    pps = prods / (ms * 1e-3)
+    val = pps / full_p0
+    cores = ol.ref().ref_num_threads() if kind == "reference" else 1
+    sample = ("%s: %d iterations, %d products in %.1f ms = %.3g products/s (%.3f iter/s there); value = that rate / "
+              "the full workload's first-iteration products %d" % (desc_s, iters, prods, ms, pps, iters / (ms * 1e-3), full_p0))
+    print(json.dumps({
+        "impl": "reference", "metric": RMCL_METRIC, "value": val, "unit": RMCL_UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "timing": "omp_get_wtime around the reference's mtRmclIter (SOMP)"},
+        "cpu_baseline": {"value": val, "unit": RMCL_UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": RMCL_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
 # ---- GPU arm -----------------------------------------------------------------------------------
 
 def kernel_bytes(kind, rows, products, nnzA, nnzC):
@@ -280,7 +537,10 @@ def run_b200(args):
             raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # (NCCL prints its version banner on stdout when the first communicator is created)
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     smf.init(local)  # raises without a CUDA device: there is no CPU fallback
     lib = _lib.load()
     sp = C.c_void_p()
@@ -291,6 +551,17 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    env = {"smf": smf, "lib": lib, "stream": stream, "barrier": barrier, "rank": rank, "world": world,
+           "local": local}
+    if args.workload.startswith("rmcl-"):
+        line = rmcl_measure(args, env, args.workload, args.steps, args.warmup, not args.no_cpu, not args.no_e2e)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            smf.comm_destroy()
+            dist.destroy_process_group()
+        return
 
     A, desc = make_workload(smf, args.workload)
     dA = A.toGpuCSR()
@@ -404,6 +675,19 @@ def run_b200(args):
         cpu = {"value": arm.gflops(ms), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                "sample": arm.sample, "ms": ms}
 
+    # ---- the second half of the BASELINE metric: rMCL iterations / second, same process and GPUs
+    rmcl = None
+    if args.rmcl_leg != "none":
+        dA.deviceDispose()
+        dA = None
+        try:
+            r = rmcl_measure(args, env, args.rmcl_leg, max(1, min(args.steps, 2)), 1, not args.no_cpu,
+                             not args.no_e2e)
+            rmcl = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config",
+                                      "roofline", "cpu_baseline", "e2e", "gpu_launches")}
+        except Exception as e:  # noqa: BLE001 — the headline line must still be printed
+            rmcl = {"metric": RMCL_METRIC, "value": None, "error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -415,11 +699,14 @@ def run_b200(args):
                        "l2": "no flush: inputs (%.0f MB) and output exceed the %d MB L2" % (
                            (12 * A.nnz + 8 * A.rows) / 1e6, L2_BYTES // (1024 * 1024))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks,
+            "clocks": clocks, "rmcl": rmcl,
         }
         print(json.dumps(line), flush=True)
-    dA.deviceDispose()
+    if dA is not None:
+        dA.deviceDispose()
     if world > 1:
+        if env.get("comm"):
+            smf.comm_destroy()
         dist.destroy_process_group()
 
 
@@ -435,8 +722,11 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     from sparse_matrix_with_flops_b200 import _lib
     ip, dp = _lib.c_int_p, _lib.c_double_p
     h2d = d2h = nblk = 0
-    rp = A.rowPtr[lo:hi + 1]
     same = lo == 0 and hi == A.rows
+    # this rank's row block of A as a CSR of its own (row offsets from 0, its slice of JA / A)
+    z0, z1 = int(A.rowPtr[lo]), int(A.rowPtr[hi])
+    rp = np.ascontiguousarray(A.rowPtr[lo:hi + 1] - A.rowPtr[lo]).astype(np.int32)
+    blkJ, blkV = A.colInd[z0:z1], A.values[z0:z1]
 
     @_lib.block_fn
     def sink(_user, r0, r1, IC, JC, Cv, nnzC):
@@ -450,14 +740,23 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     def one_streamed():
         nonlocal h2d, d2h, nblk
         d2h = nblk = 0
-        h2d = 4 * (hi - lo + 1) + 12 * A.nnz + (0 if same else 4 * (A.rows + 1) + 12 * A.nnz)
-        _lib.check(lib.b200_spgemm_csr_stream(
-            rp.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
-            A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
-            hi - lo, A.cols, A.cols, 0, sink, None))
+        h2d = 4 * (hi - lo + 1) + 12 * (z1 - z0) + (0 if same else 4 * (A.rows + 1) + 12 * A.nnz)
+        if same:   # the very same arrays on both sides: the library uploads them once
+            _lib.check(lib.b200_spgemm_csr_stream(
+                A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
+                A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
+                A.rows, A.cols, A.cols, 0, sink, None))
+        else:
+            _lib.check(lib.b200_spgemm_csr_stream(
+                rp.ctypes.data_as(ip), blkJ.ctypes.data_as(ip), blkV.ctypes.data_as(dp), z1 - z0,
+                A.rowPtr.ctypes.data_as(ip), A.colInd.ctypes.data_as(ip), A.values.ctypes.data_as(dp), A.nnz,
+                hi - lo, A.rows, A.cols, 0, sink, None))
 
-    # N > 1: the sequence measured on 2 / 4 / 8 GPUs in profiles/ — CSR::toGpuCSR of the whole
-    # matrix, gpuSpMMWrapper on this rank's row blocks, CSR::toCpuCSR of each block
+    # N > 1: CSR::toGpuCSR of the whole matrix, gpuSpMMWrapper on this rank's row blocks,
+    # CSR::toCpuCSR of each block.  (The streamed call per rank was measured too, round 2, N = 2:
+    # 8.5 GFLOP/s against 16.4 for this sequence — the ranks share the host's 16 cores, and the
+    # streamed path's helper thread and staging copies of one rank then compete with the other
+    # rank's kernels' host side)
     prefix = host_flops_prefix(A)
     mine = int(prefix[hi] - prefix[lo])
     nblk_seq = max(1, -(-mine // 2_000_000_000))
@@ -521,7 +820,7 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
 def main():
     args = parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_rmcl if args.workload.startswith("rmcl-") else run_reference)(args)
     else:
         run_b200(args)
 

@@ -213,24 +213,14 @@ int b200_comm_destroy(void);
  * on every rank (the old handle is freed). */
 int b200_rmcl_iter_sharded(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* Mt_io,
                            int* iters_done, double* chaos_hist, double* ms_per_iter);
-/* The same loop; counts_per_iter (may be NULL; room for 4 * maxIter values) receives per
+/* The same loop; counts_per_iter (may be NULL; room for 5 * maxIter values) receives per
  * iteration {intermediate products of the whole step, nnz of the new Mt, its unpruned nnz summed
- * over the ranks, most row tiles any rank ran the step in} — what a harness needs for the
- * roofline of an iteration. */
+ * over the ranks, most row tiles any rank ran the step in, kernels this rank launched} — what a
+ * harness needs for the roofline of an iteration. */
 int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_csr_t* Mt_io,
                                  int* iters_done, double* chaos_hist, double* ms_per_iter,
                                  long long* counts_per_iter);
 
-/* ---- synthetic inputs (harness) ---------------------------------------- *
- * All return a malloc()'d int CSR with rmclInit semantics (nlibs/qrmcl.cc:126-134): self loop
- * on every vertex, sorted unique columns, values 1/rowcount.  Release with b200_host_free. */
-int b200_synth_rmat(int scale, int edge_factor, unsigned long long seed, int symmetrise,
-                    int* rows, int** IA, int** JA, double** A, long long* nnz);
-int b200_synth_stencil27(int gx, int gy, int gz, int* rows, int** IA, int** JA, double** A,
-                         long long* nnz);
-int b200_synth_planted(int n, int nblocks, int intra, int inter, unsigned long long seed,
-                       int* rows, int** IA, int** JA, double** A, long long* nnz,
-                       int** labels);
 /* Releases a malloc()'d block returned by this library.  Large blocks (>= 64 MB) are kept for
  * the next download instead of going back to the OS, up to B200_HOST_CACHE_GB (environment;
  * default a quarter of the physical memory, at most 64 GB; 0 = never keep): the first touch of

@@ -106,6 +106,14 @@ SIGNATURES = {
                                          c_double_p, c_double_p]),
     "b200_rmcl_iter_sharded_stats": (C.c_int, [C.c_int, C.c_double, csr_t, C.POINTER(csr_t), c_int_p,
                                                c_double_p, c_double_p, c_ll_p]),
+    "b200_host_free": (None, [C.c_void_p]),
+    "b200_host_cache_info": (C.c_int, [c_ll_p, c_int_p, c_ll_p]),
+    "b200_host_cache_drop": (C.c_int, []),
+}
+
+# harness-only generators: libb200synth.so (include/b200_synth.h), host code
+SYNTH_PATH = os.path.join(_HERE, "libb200synth.so")
+SYNTH_SIGNATURES = {
     "b200_synth_rmat": (C.c_int, [C.c_int, C.c_int, C.c_ulonglong, C.c_int, c_int_p,
                                   C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p), c_ll_p]),
     "b200_synth_stencil27": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(c_int_p),
@@ -113,12 +121,28 @@ SIGNATURES = {
     "b200_synth_planted": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, c_int_p,
                                      C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p),
                                      c_ll_p, C.POINTER(c_int_p)]),
-    "b200_host_free": (None, [C.c_void_p]),
-    "b200_host_cache_info": (C.c_int, [c_ll_p, c_int_p, c_ll_p]),
-    "b200_host_cache_drop": (C.c_int, []),
 }
 
 _lib = None
+_synth = None
+
+
+def load_synth():
+    """Load the generator library (host code only; no CUDA, no product code)."""
+    global _synth
+    if _synth is not None:
+        return _synth
+    if not os.path.exists(SYNTH_PATH):
+        raise ImportError(f"{SYNTH_PATH} is missing: build it with `make -C sparse_matrix_with_flops_b200/csrc`")
+    lib = C.CDLL(SYNTH_PATH)
+    for name, (res, args) in SYNTH_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.free.restype = None
+    lib.free.argtypes = [C.c_void_p]
+    _synth = lib
+    return lib
 
 
 def load():

@@ -292,13 +292,13 @@ def gpuRmclIterSharded(maxIter, dMgt, dMt, eps=0.0, want_counts=False):
     ms = np.zeros(max(1, maxIter), dtype=np.float64)
     if not isinstance(dMt.handle, csr_t):
         dMt.handle = csr_t(dMt.handle)
-    counts = np.zeros(4 * max(1, maxIter), dtype=np.int64)
+    counts = np.zeros(5 * max(1, maxIter), dtype=np.int64)
     check(lib.b200_rmcl_iter_sharded_stats(int(maxIter), float(eps), dMgt.handle, C.byref(dMt.handle),
                                            C.byref(iters), _dp(hist), _dp(ms),
                                            counts.ctypes.data_as(_lib.c_ll_p) if want_counts else None))
     out = (iters.value, hist[:iters.value].copy(), ms[:iters.value].copy())
-    if want_counts:   # per iteration: products, nnz(new Mt), unpruned nnz, row tiles
-        out += (counts.reshape(-1, 4)[:iters.value].copy(),)
+    if want_counts:   # per iteration: products, nnz(new Mt), unpruned nnz, row tiles, launches
+        out += (counts.reshape(-1, 5)[:iters.value].copy(),)
     return out
 
 
@@ -377,34 +377,51 @@ def arrayEqualPartition64(prefix, nparts):
 
 # ---- synthetic inputs --------------------------------------------------------
 
-def _synth_out(n, I, J, V, nnz):
-    return CSR(_take(V, nnz, np.float64), _take(J, nnz, np.int32), _take(I, n + 1, np.int32), n, n, nnz)
+# ---- synthetic inputs: libb200synth.so (harness code; the product library is not involved) ----
+
+def _take_plain(lib, ptr, count, dtype):
+    out = (np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True) if count > 0
+           else np.zeros(0, dtype=dtype))
+    lib.free(C.cast(ptr, C.c_void_p))
+    return out
+
+
+def _synth_check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed with code %d" % (what, rc))
+
+
+def _synth_out(lib, n, I, J, V, nnz):
+    return CSR(_take_plain(lib, V, nnz, np.float64), _take_plain(lib, J, nnz, np.int32),
+               _take_plain(lib, I, n + 1, np.int32), n, n, nnz)
 
 
 def synth_rmat(scale, edge_factor=16, seed=12345, symmetrise=False):
-    lib = _lib.load()
+    lib = _lib.load_synth()
     n, nnz = C.c_int(), C.c_longlong()
     I, J, V = c_int_p(), c_int_p(), c_double_p()
-    check(lib.b200_synth_rmat(scale, edge_factor, seed, int(symmetrise), C.byref(n), C.byref(I),
-                              C.byref(J), C.byref(V), C.byref(nnz)))
-    return _synth_out(n.value, I, J, V, nnz.value)
+    _synth_check(lib.b200_synth_rmat(scale, edge_factor, seed, int(symmetrise), C.byref(n), C.byref(I),
+                                     C.byref(J), C.byref(V), C.byref(nnz)), "b200_synth_rmat")
+    return _synth_out(lib, n.value, I, J, V, nnz.value)
 
 
 def synth_stencil27(gx, gy, gz):
-    lib = _lib.load()
+    lib = _lib.load_synth()
     n, nnz = C.c_int(), C.c_longlong()
     I, J, V = c_int_p(), c_int_p(), c_double_p()
-    check(lib.b200_synth_stencil27(gx, gy, gz, C.byref(n), C.byref(I), C.byref(J), C.byref(V), C.byref(nnz)))
-    return _synth_out(n.value, I, J, V, nnz.value)
+    _synth_check(lib.b200_synth_stencil27(gx, gy, gz, C.byref(n), C.byref(I), C.byref(J), C.byref(V),
+                                          C.byref(nnz)), "b200_synth_stencil27")
+    return _synth_out(lib, n.value, I, J, V, nnz.value)
 
 
 def synth_planted(n, nblocks, intra=16, inter=2, seed=12345, want_labels=False):
-    lib = _lib.load()
+    lib = _lib.load_synth()
     rows, nnz = C.c_int(), C.c_longlong()
     I, J, V, L = c_int_p(), c_int_p(), c_double_p(), c_int_p()
-    check(lib.b200_synth_planted(n, nblocks, intra, inter, seed, C.byref(rows), C.byref(I), C.byref(J),
-                                 C.byref(V), C.byref(nnz), C.byref(L) if want_labels else None))
-    out = _synth_out(rows.value, I, J, V, nnz.value)
+    _synth_check(lib.b200_synth_planted(n, nblocks, intra, inter, seed, C.byref(rows), C.byref(I), C.byref(J),
+                                        C.byref(V), C.byref(nnz), C.byref(L) if want_labels else None),
+                 "b200_synth_planted")
+    out = _synth_out(lib, rows.value, I, J, V, nnz.value)
     if want_labels:
-        return out, _take(L, n, np.int32)
+        return out, _take_plain(lib, L, n, np.int32)
     return out

@@ -176,6 +176,7 @@ int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_c
                                        counts_per_iter ? &bst : nullptr);
       long long unpruned = (counts_per_iter && !lrc) ? bst.nnz_unpruned : 0;
       long long tiles = (counts_per_iter && !lrc) ? std::max(1, bst.row_tiles) : 0;
+      const long long launches = (counts_per_iter && !lrc) ? bst.launches : 0;
       CsrGuard next;
       if (R == 1) {
         if (lrc) return lrc;
@@ -243,10 +244,11 @@ int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_c
       if (ms_per_iter) { float ms = 0; cudaEventElapsedTime(&ms, ev.e0, ev.e1); ms_per_iter[it] = ms; }
       if (chaos_hist) chaos_hist[it] = ch;
       if (counts_per_iter) {
-        counts_per_iter[4 * it + 0] = P_total;
-        counts_per_iter[4 * it + 1] = cur.nnz;
-        counts_per_iter[4 * it + 2] = unpruned;
-        counts_per_iter[4 * it + 3] = tiles;
+        counts_per_iter[5 * it + 0] = P_total;
+        counts_per_iter[5 * it + 1] = cur.nnz;
+        counts_per_iter[5 * it + 2] = unpruned;
+        counts_per_iter[5 * it + 3] = tiles;
+        counts_per_iter[5 * it + 4] = launches;
       }
       if (rmcl_converged(ch, prev_ch, it, eps)) { ++it; break; }
       prev_ch = ch;

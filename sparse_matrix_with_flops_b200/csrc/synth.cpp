@@ -20,7 +20,11 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
-#include "b200_spgemm.h"
+#include "b200_synth.h"
+
+// return codes: the values of include/b200_spgemm.h (0 ok, 1 bad argument, 3 host allocation,
+// 4 does not fit int32), repeated here so that this library does not depend on the product's
+enum { B200_OK = 0, B200_ERR_BAD_ARG = 1, B200_ERR_HOST_ALLOC = 3, B200_ERR_INT32_OVERFLOW = 4 };
 
 namespace {
 

@@ -121,6 +121,11 @@ static long long arena_budget_entries() {
   Ctx& c = ctx();
   if (c.tun.arena_entries > 0) return c.tun.arena_entries;
   if (c.arena_budget == 0) {
+    // blocks an earlier call freed (a 100 GB product, say) sit in the stream-ordered pool: give
+    // them back first, or they would count as used
+    cudaStreamSynchronize(c.stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     // 40 % of what is free now plus what the arena already holds; the operands, the result and

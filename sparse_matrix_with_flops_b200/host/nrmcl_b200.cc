@@ -11,6 +11,7 @@
 #include <chrono>
 #include <set>
 #include "b200_nlibs.hpp"
+#include "b200_synth.h"   // harness-only generators (libb200synth.so)
 
 using namespace b200::nlibs;
 

@@ -24,6 +24,14 @@ def test_every_declared_symbol_is_exported(smf):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/b200_spgemm.h but not exported"
     assert declared == set(smf._lib.SIGNATURES), declared ^ set(smf._lib.SIGNATURES)
+    # the harness-only generator library has its own header; none of it lives in the product
+    header = open(os.path.join(ROOT, "include", "b200_synth.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    synth = smf._lib.load_synth()
+    for name in sorted(declared):
+        assert hasattr(synth, name), f"{name} declared in include/b200_synth.h but not exported"
+        assert not hasattr(lib, name), f"{name}: generators must stay out of the product library"
+    assert declared == set(smf._lib.SYNTH_SIGNATURES)
 
 
 def test_no_cpu_fallback(smf):

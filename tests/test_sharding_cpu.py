@@ -80,17 +80,25 @@ def test_bench_helpers(smf):
         assert np.array_equal(J[I[k]:I[k + 1]], A.colInd[A.rowPtr[r]:A.rowPtr[r + 1]])
     # algorithmic bytes of a numeric launch
     assert bench.kernel_bytes("num", 10, 1000, 100, 500) == 12 * 100 + 40 + 12 * 1000 + 800 + 6000 + 40
+    # ... and of one fused rMCL iteration: the same with the PRUNED nnz on the output side
+    assert bench.rmcl_iter_bytes(9, 100, 1000, 50) == 12 * 100 + 40 + 12 * 1000 + 800 + 600 + 40
+    A2, desc, small = bench.make_rmcl_workload(smf, "rmcl-rmat9e4")
+    assert A2.rows == 512 and small == "rmcl-rmat9e4" and "symmetrised" in desc
+    assert bench.make_rmcl_workload(smf, "rmcl-planted400000c100")[2] == "rmcl-planted100000c25"
 
 
-def test_reference_arm_prints_the_contract_line():
+@pytest.mark.parametrize("workload,metric", [("rmat10", "spgemm_gflops"), ("rmcl-rmat10", "rmcl_iters_per_s"),
+                                             ("rmcl-planted3000c10", "rmcl_iters_per_s")])
+def test_reference_arm_prints_the_contract_line(workload, metric):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                          "--workload", "rmat10", "--steps", "1", "--warmup", "1"],
+                          "--workload", workload, "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
+    assert len(out.stdout.strip().splitlines()) == 1, "exactly one line on stdout"
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
                 "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["metric"] == "spgemm_gflops" and line["value"] > 0
+    assert line["impl"] == "reference" and line["metric"] == metric and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
