@@ -49,12 +49,9 @@ struct Tunables {
   long long team_products = 98304;  // B200_TEAM_P, B200_TEAM_MAX: team sizing of the part kernel
   int team_max = 64;
   long long arena_entries = 0;  // B200_ARENA_ENTRIES: products per row tile of an rMCL step (0: from free memory)
-  int ranges = 64;      // B200_RANGES: static column ranges of the on-chip numeric pass (2..64)
-  int chunk_min = 96;   // B200_CHUNK_MIN: items whose expected B-row segments are shorter do not
-                        // commit in A-entry order (a barrier per segment) but by tag arbitration
-  bool no_tag = false;  // B200_NO_TAG: ... or with global RED instead (A/B switch)
-  bool deterministic = false;  // B200_DETERMINISTIC: every on-chip item in A-entry order (bit-exact,
-                               // reproducible; slower on rows with thousands of short segments)
+  int ranges = 128;     // B200_RANGES: static column ranges of the on-chip numeric pass (2..128)
+  bool deterministic = false;  // B200_DETERMINISTIC: B200_ON_CHIP (heavy rows accumulate on chip in
+                               // A-entry order: bit-identical to the reference, reproducible)
 };
 void load_tunables(Tunables* t);
 

@@ -1,5 +1,7 @@
-// ranges.cuh — numeric pass of the heavy rows with ON-CHIP accumulation (included by spgemm.cu,
-// inside its anonymous namespace).
+// ranges.cuh — numeric pass of the heavy rows with ON-CHIP, ORDERED accumulation (included by
+// spgemm.cu, inside its anonymous namespace).  Opt-in (B200_ON_CHIP / B200_DETERMINISTIC): it
+// reproduces the reference's values bit for bit and run to run, at 1.2 - 1.5x the time of the
+// default part kernel (global fp64 RED) on R-MAT scale 20 — DESIGN.md §3b has the measurements.
 //
 // Reference behaviour being replaced: indexProcessCRowI, nlibs/cpu_csr_kernel.h:134-188 — one
 // dense accumulator per output row, products added in (A entry, B entry) order.
@@ -12,31 +14,15 @@
 // counts the output columns of every heavy row per range (rcnt).  A planner then groups
 // consecutive ranges of a row into work ITEMS whose accumulators (8 B per output column) and
 // column index (16 B per 64 columns: {32 bitmap bits, 32-bit rank prefix} pairs, so one
-// shared-memory load gives the rank of a column) fit the shared-memory pool of a CTA.
-//
-// An item is handled by one CTA (k_num_items):
-//   table     the B-row segment [start, start+len) of every A entry inside the item's ranges
-//             (two loads from the split table, no search), padded to whole warp slots;
-//   window    the item's bitmap words from the store of the symbolic pass -> packed pairs;
-//   products  a flat, coalesced walk over the segments, loads three steps ahead of use.  Every
-//             lane looks up its rank, then the segments COMMIT IN A-ENTRY ORDER: a B row has
-//             unique columns, so the lanes of one segment update distinct accumulators with a
-//             plain shared-memory load / add / store (no atomics: shared atomics cost 2 cycles
-//             per lane, a global RED 1.3), and a barrier separates consecutive segments.  Every
-//             output entry therefore sums its products in ascending A-entry order with
-//             separately rounded multiply and add — the order and rounding of the reference:
-//             the values are BIT-IDENTICAL to indexProcessCRowI, and run-to-run reproducible;
-//   flush     values and columns leave through shared memory as coalesced streams.
-// Items whose segments are too short for that (hub rows: thousands of A entries, a dozen
-// products each per range) or whose single range overflows the pool run in RED mode: same
-// table / window / walk, accumulators in the row's final slice of C.val (zeroed first), one
-// fp64 RED per product, order not fixed (values to rounding).
+// shared-memory load gives the rank of a column) fit the shared-memory pool of ONE WARP
+// (k_num_units, below).  An item whose single range overflows the pool keeps its accumulators in
+// the row's final slice of C.val (zeroed first) and uses one fp64 RED per product.
 
-constexpr int RANGES_MAX = 64;
-// how an item accumulates: on chip with the segments committed in A-entry order (bit-exact), in
-// HBM with fp64 RED, or on chip with tag arbitration (order not fixed)
-constexpr int ITEM_ORD = 0, ITEM_RED = 1, ITEM_TAG = 2;
-constexpr int SLOTS_MAX = 2048;  // lane groups (32 or 8 lanes) of one table batch
+constexpr int RANGES_MAX = 128;
+// how an item accumulates: on chip, B-row segments in A-entry order (bit-exact), or — when one
+// range alone overflows the warp's pool — in HBM with fp64 RED (order not fixed); with
+// B200_DETERMINISTIC such a range is instead walked once per pool-sized piece of its columns
+constexpr int ITEM_ORD = 0, ITEM_RED = 1, ITEM_MULTI = 2;  // MULTI: on chip, in several column passes
 
 // Everything the kernel needs to start an item, so that an item costs ONE dependent load (its
 // descriptor, fetched while the previous item is being processed).
@@ -150,8 +136,7 @@ k_range_split(const int64_t* __restrict__ Brp, const int* __restrict__ Bcol, int
 // pass 1 writes them at itemoff[t].
 struct PlanCtx {
   const int* rw;
-  int R, pool_bytes, chunk_min, nw64, short_mode;
-  double seg_per_range;  // expected products of one A entry inside one range
+  int R, pool_bytes, nw64, deterministic;
   long long a0, ob, bmrow;
   int nA;
   RangeItem* out;
@@ -183,10 +168,7 @@ __device__ __forceinline__ int plan_row(const int* __restrict__ rc, const PlanCt
     pcnt = 0;
   };
   auto emit = [&](int a, int b, int cnt, bool forced_red) {
-    // expected products of one A entry inside the group: long segments commit in order (a
-    // barrier per segment pays above ~100 products), short ones use tag arbitration (or RED)
-    const bool is_short = pc.seg_per_range * (b - a) < (double)pc.chunk_min;
-    const int mode = forced_red ? ITEM_RED : (is_short ? pc.short_mode : ITEM_ORD);
+    const int mode = forced_red ? (pc.deterministic ? ITEM_MULTI : ITEM_RED) : ITEM_ORD;
     if (mode != ITEM_RED) { flush_red(); write(a, b, cnt, mode); return; }
     if (pr0 >= 0 && 16 * (pc.rw[b] - pc.rw[pr0]) > pc.pool_bytes) flush_red();
     if (pr0 < 0) pr0 = a;
@@ -199,13 +181,13 @@ __device__ __forceinline__ int plan_row(const int* __restrict__ rc, const PlanCt
   for (int r = 0; r < pc.R; ++r) {
     const int cr = rc[r];
     if (cr == 0) continue;
-    if (c > 0 && 10 * (c + cr) + 16 * (pc.rw[r + 1] - pc.rw[r0]) > pc.pool_bytes) {
+    if (c > 0 && 8 * (c + cr) + 16 * (pc.rw[r + 1] - pc.rw[r0]) > pc.pool_bytes) {
       emit(r0, rend, c, false);
       c = 0;
     }
     if (c == 0) {
       r0 = r;
-      if (10 * cr + 16 * (pc.rw[r + 1] - pc.rw[r]) > pc.pool_bytes) {
+      if (8 * cr + 16 * (pc.rw[r + 1] - pc.rw[r]) > pc.pool_bytes) {
         emit(r, r + 1, cr, true);  // one range overflows the pool: its accumulators stay in HBM
         continue;
       }
@@ -221,7 +203,7 @@ __device__ __forceinline__ int plan_row(const int* __restrict__ rc, const PlanCt
 __global__ void __launch_bounds__(256)
 k_plan_items(const int* __restrict__ list, int count, const int* __restrict__ bm_slot,
              const int* __restrict__ rcnt, const int* __restrict__ rw, int R, int pool_bytes,
-             int chunk_min, int short_mode, int nw64, const long long* __restrict__ flops,
+             int nw64, int deterministic,
              const int64_t* __restrict__ Arp, int row_lo, const int64_t* __restrict__ Crp,
              int* __restrict__ nitems, const int* __restrict__ itemoff,
              RangeItem* __restrict__ items, int* __restrict__ fb_list, int* __restrict__ fb_count) {
@@ -234,10 +216,9 @@ k_plan_items(const int* __restrict__ list, int count, const int* __restrict__ bm
     return;
   }
   PlanCtx pc;
-  pc.rw = rw; pc.R = R; pc.pool_bytes = pool_bytes; pc.chunk_min = chunk_min; pc.nw64 = nw64; pc.short_mode = short_mode;
+  pc.rw = rw; pc.R = R; pc.pool_bytes = pool_bytes; pc.nw64 = nw64; pc.deterministic = deterministic;
   pc.a0 = Arp[row_lo + i];
   pc.nA = (int)(Arp[row_lo + i + 1] - pc.a0);
-  pc.seg_per_range = (double)flops[i] / (double)max(1, pc.nA) / (double)R;
   pc.ob = Crp[i];
   pc.bmrow = (long long)slot * nw64;
   pc.out = items ? items + itemoff[t] : nullptr;
@@ -246,303 +227,228 @@ k_plan_items(const int* __restrict__ list, int count, const int* __restrict__ bm
 }
 
 // ---- the item kernel ----------------------------------------------------------------------
-template <int BT>
-struct ItemSmem {
-  long long start[BT];  // first B entry of the segment
-  double a[BT];         // A value of the entry
-  int ws[BT + 1];       // first warp slot of the segment (exclusive scan of the slot counts)
-  int len[BT];          // products of the segment
-  unsigned short eslot[SLOTS_MAX];  // warp slot -> segment
-  int red[BT / 32 + 2];
-  int next[12];         // descriptor of this CTA's next item (fetched one item ahead)
-  // staging ring of the product walk: every thread copies its own (column, value) of the steps
-  // s+1 .. s+3 with cp.async while step s is being accumulated
-  int rcol[3][BT];
-  double rval[3][BT];
-};
+// One WARP per item, warp-synchronous from start to end: no block barrier, no atomics, no shared
+// state between warps.  A 128-thread CTA is four independent workers with a quarter of the
+// CTA's shared memory each; four CTAs per SM give 16 workers whose latencies overlap.
+//   window   the item's bitmap words -> {32 bits, rank prefix} pairs in the warp's pool;
+//   walk     the A entries 32 at a time (lane = entry: its B-row segment inside the item's ranges
+//            comes from two adjacent loads of the split table), then the segments ONE AT A TIME,
+//            lanes across a segment: a B row has unique columns, so the lanes update distinct
+//            accumulators with a plain shared-memory load / add / store, and every output entry
+//            sums its products in ascending A-entry order with separately rounded multiply and
+//            add — indexProcessCRowI's order and rounding (cpu_csr_kernel.h:159-170): the values
+//            are bit-identical to the reference's and reproducible.  Loads of four segment
+//            chunks are issued together before the first of them is used;
+//   flush    values, then the columns (expanded from the window into the same pool), as
+//            coalesced streams.
+constexpr int UNIT_WARPS = 4;     // workers per CTA
+constexpr int UNIT_CHUNK = 4;     // items a worker draws per ticket
+constexpr int UNIT_DEPTH = 8;     // segment chunks whose loads are in flight together
 
-// Items are dealt round-robin to the CTAs (they are bounded in size and there are thousands per
-// CTA, so a dynamic ticket buys nothing): the next item of a CTA is known, its descriptor is
-// fetched and its window / A entries are requested from L2 while the current item runs.
-template <int BT, int MINB>
-__global__ void __launch_bounds__(BT, MINB)
-k_num_items(const RangeItem* __restrict__ items, int nitems, int R,
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 4)
+k_num_units(const RangeItem* __restrict__ items, int nitems, int R, int pool_bytes,
             const int* __restrict__ Acol, const double* __restrict__ Aval,
             const int64_t* __restrict__ Brp, const int* __restrict__ Bcol,
             const double* __restrict__ Bval, const unsigned* __restrict__ split,
             const unsigned long long* __restrict__ bm_store, int* __restrict__ Ccol,
-            double* __restrict__ Cval, L2Modes l2, unsigned long long* __restrict__ prof) {
+            double* __restrict__ Cval, int* __restrict__ work_counter, L2Modes l2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NW = BT / 32;
-  // developer diagnostics (B200_PROF): cycles per phase, summed over this CTA's items
-  long long pcyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tsub = 0;
-  auto sub = [&](int k) {
-    if (prof && threadIdx.x == 0) { const long long t = clock64(); pcyc[k] += t - tsub; tsub = t; }
-  };
-  long long tprev = 0;
-  auto lap = [&](int k) {
-    if (prof && threadIdx.x == 0) { const long long t = clock64(); pcyc[k] += t - tprev; tprev = t; }
-  };
-  ItemSmem<BT>& sm = *reinterpret_cast<ItemSmem<BT>*>(smem_raw);
-  unsigned char* pool = smem_raw + ((sizeof(ItemSmem<BT>) + 15) & ~(size_t)15);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* pool = smem_raw + (size_t)warp * pool_bytes;
   const unsigned long long pol_acc = l2_policy(l2.acc), pol_out = l2_policy(L2_FIRST),
                            pol_b = l2_policy(l2.bgather), pol_bm = l2_policy(l2.bmstore);
-  if ((int)blockIdx.x < nitems && threadIdx.x < 12)
-    sm.next[threadIdx.x] = reinterpret_cast<const int*>(items + blockIdx.x)[threadIdx.x];
-  for (int t = blockIdx.x; t < nitems; t += gridDim.x) {
-    __syncthreads();
-    if (prof && threadIdx.x == 0) tprev = clock64();
-    RangeItem it;
-    {
-      int* d = reinterpret_cast<int*>(&it);
-#pragma unroll
-      for (int k = 0; k < 12; ++k) d[k] = sm.next[k];
-    }
-    __syncthreads();
-    // the descriptor after this one: loaded now, parked in shared memory at the end of the item
-    const int tn = t + gridDim.x;
-    int nx = 0;
-    if (tn < nitems && threadIdx.x < 12) nx = __ldg(reinterpret_cast<const int*>(items + tn) + threadIdx.x);
-    const int r0 = it.desc & 255, r1 = (it.desc >> 8) & 255, mode = it.desc >> 16;
-    const int cnt = it.cnt, W = it.W, c_lo = it.c_lo;
-    const int64_t a0 = it.a0, a1 = it.a0 + it.nA;
-    const int64_t ob = it.ob;
-    const bool on_chip = mode != ITEM_RED;
-    // lanes per slot of the flat walk: whole warps when segments commit in order, 8-lane groups
-    // otherwise (a 13-product segment padded to 32 lanes would idle most of them)
-    const int gsh = mode == ITEM_ORD ? 5 : 3;
-    const int GPS = BT >> gsh;  // slots per step
-    // pool: accumulators (on-chip modes), the packed window, the tags (tag mode)
-    double* acc = reinterpret_cast<double*>(pool);
-    const size_t acc_bytes = on_chip ? (((size_t)cnt * 8 + 15) & ~(size_t)15) : 0;
-    uint2* pk = reinterpret_cast<uint2*>(pool + acc_bytes);
-    unsigned short* tag = reinterpret_cast<unsigned short*>(pool + acc_bytes + (size_t)W * 16);
-    // ---- window: bitmap words -> {bits of 32 columns, rank of the first of them}.  Pass 1:
-    // every word fetched with independent loads (one round trip to HBM for the whole window);
-    // pass 2: the popcount prefix from shared memory, warp w owning a contiguous run.
-    {
-      const unsigned long long* src = bm_store + it.bmoff;
-      for (int w = threadIdx.x; w < W; w += BT) {
-        const unsigned long long x = ldg_hint(src + w, pol_bm);
-        pk[2 * w].x = (unsigned)x;
-        pk[2 * w + 1].x = (unsigned)(x >> 32);
+  // descriptor fields travel one per lane: lanes 0..11 hold the current item's, 16..27 the next's
+  auto field = [&](int dv, int k) { return __shfl_sync(FULL, dv, k); };
+  auto field64 = [&](int dv, int k) {
+    return ((long long)__shfl_sync(FULL, dv, k + 1) << 32) | (unsigned)__shfl_sync(FULL, dv, k);
+  };
+  while (true) {
+    int t0 = 0;
+    if (lane == 0) t0 = atomicAdd(work_counter, UNIT_CHUNK);
+    t0 = __shfl_sync(FULL, t0, 0);
+    if (t0 >= nitems) break;
+    const int t1 = min(nitems, t0 + UNIT_CHUNK);
+    for (int t = t0; t < t1; ++t) {
+      int dv = 0;
+      {
+        const int k = lane & 15, tt = t + (lane >> 4);
+        if (k < 12 && tt < t1) dv = __ldg(reinterpret_cast<const int*>(items + tt) + k);
       }
-      // accumulators zeroed under the shadow of those loads
-      if (on_chip) {
-        for (int k = threadIdx.x; k < cnt; k += BT) acc[k] = 0.0;
-      } else {
-        for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(Cval + ob + k, 0.0, pol_acc);
-      }
-      __syncthreads();
-      const int wpw = (((W + NW - 1) / NW) + 31) & ~31;
-      const int wbeg = warp * wpw, wend = min(W, wbeg + wpw);
-      int run = 0;
-      for (int w = wbeg + lane; w < wbeg + wpw; w += 32) {
-        unsigned lo32 = 0, hi32 = 0;
-        if (w < wend) { lo32 = pk[2 * w].x; hi32 = pk[2 * w + 1].x; }
-        const int cl = __popc(lo32), c = cl + __popc(hi32);
-        int inc = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(FULL, inc, o);
-          if (lane >= o) inc += y;
-        }
-        if (w < wend) {
-          const unsigned ex = (unsigned)(run + inc - c);
-          pk[2 * w].y = ex;
-          pk[2 * w + 1].y = ex + cl;
-        }
-        run += __shfl_sync(FULL, inc, 31);
-      }
-      if (lane == 0) sm.red[warp] = run;
-      __syncthreads();
-      int wbase = 0;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) wbase += (k < warp) ? sm.red[k] : 0;
-      if (wbase)
-        for (int w = wbeg + lane; w < wend; w += 32) { pk[2 * w].y += wbase; pk[2 * w + 1].y += wbase; }
-    }
-    double* gacc = Cval + ob;
-    lap(0);
-    // ---- products: batches of up to BT A entries (fewer when their slots exceed the table)
-    int e_prev = -1;  // last segment committed by this CTA (barriers separate segments)
-    for (int64_t b0 = a0; b0 < a1;) {
-      int nb = (int)min((int64_t)BT, a1 - b0);
-      int myslots = 0;
-      if ((int)threadIdx.x < nb) {
-        const int j = __ldg(Acol + b0 + threadIdx.x);
-        const long long rp = __ldg(Brp + j);
-        const unsigned* sp = split + (size_t)j * R;
-        const long long o0 = (r0 == 0) ? 0 : (long long)__ldg(sp + r0 - 1);
-        const long long o1 = (r1 == R) ? (__ldg(Brp + j + 1) - rp) : (long long)__ldg(sp + r1 - 1);
-        sm.start[threadIdx.x] = rp + o0;
-        sm.len[threadIdx.x] = (int)(o1 - o0);
-        sm.a[threadIdx.x] = __ldg(Aval + b0 + threadIdx.x);
-        myslots = (int)((o1 - o0 + (1 << gsh) - 1) >> gsh);
-      }
-      int total;
-      const int ex = block_excl_scan<BT>(myslots, sm.red, &total);  // barriers inside
-      // entries whose slots fit the table; a single oversized segment is walked alone
-      bool single = false;
-      if (total > SLOTS_MAX) {
-        const int fit = __syncthreads_count((int)threadIdx.x < nb && ex + myslots <= SLOTS_MAX);
-        single = fit == 0;
-        nb = single ? 1 : fit;  // (slot counts are non-negative: the fitting entries are a prefix)
-      }
-      if ((int)threadIdx.x < nb) sm.ws[threadIdx.x] = ex;
-      if ((int)threadIdx.x == nb) sm.ws[nb] = ex;   // (thread nb exists when nb < BT)
-      if (nb == BT && threadIdx.x == 0) sm.ws[BT] = total;
-      __syncthreads();
-      const int nslots = single ? (int)((sm.len[0] + (1 << gsh) - 1) >> gsh) : sm.ws[nb];
-      if (!single)
-        for (int sl = threadIdx.x; sl < nslots; sl += BT) {
-          int lo = 0, hi = nb - 1;  // last e with ws[e] <= sl
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (sm.ws[mid] <= sl) lo = mid; else hi = mid - 1;
-          }
-          sm.eslot[sl] = (unsigned short)lo;
-        }
-      __syncthreads();
-      const int nsteps = (nslots + GPS - 1) / GPS;
-      lap(1);
-      // a stage of the staging ring.  (Register prefetch does not pipeline here: ptxas puts the
-      // loads of all stages on one scoreboard, so the first use of stage s waits for the loads
-      // of stages s+1 and s+2 as well; cp.async groups are tracked per group.)
-      const int gl = threadIdx.x >> gsh, gk = threadIdx.x & ((1 << gsh) - 1);
-      auto issue = [&](int s, int stage, int& e) {
-        const int sl = s * GPS + gl;
-        e = -1;
-        if (sl < nslots) {
-          const int ee = single ? 0 : (int)sm.eslot[sl];
-          const int k = ((sl - (single ? 0 : sm.ws[ee])) << gsh) + gk;
-          if (k < sm.len[ee]) {
-            const long long q = sm.start[ee] + k;
-            e = ee;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.rcol[stage][threadIdx.x])), "l"(Bcol + q) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.rval[stage][threadIdx.x])), "l"(Bval + q) : "memory");
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      auto consume = [&](int s, int stage, int e) {
-        int rank = 0, c = -1;
-        double prod = 0.0;
-        if (prof && threadIdx.x == 0) tsub = clock64();
-        asm volatile("cp.async.wait_group 2;" ::: "memory");  // this step's copies have landed
-        if (e >= 0) {
-          c = sm.rcol[stage][threadIdx.x];
-          const double v = sm.rval[stage][threadIdx.x];
-          const uint2 p = pk[(c - c_lo) >> 5];
-          rank = (int)p.y + __popc(p.x & ((1u << (c & 31)) - 1u));
-          prod = __dmul_rn(sm.a[e], v);
-        }
-        if (prof) { asm volatile("" ::"r"(rank), "d"(prod)); sub(4); }
-        if (mode == ITEM_RED) {
-          if (c >= 0) red_add_hint(gacc + rank, prod, pol_acc);
-        } else if (mode == ITEM_TAG) {
-          // tag arbitration: every pending lane writes its id over its accumulator's tag; after
-          // the barrier the lane that reads its own id back owns the accumulator for this pass
-          // (two lanes can never both read their own id in one pass: the tag only changes when a
-          // loser re-writes it for the next pass, which can at worst make a winner retry).
-          // Commits of consecutive passes are separated by the next pass's barrier.
-          bool pending = c >= 0;
-          while (true) {
-            if (pending) tag[rank] = (unsigned short)threadIdx.x;
-            if (!__syncthreads_or(pending)) break;
-            if (pending && tag[rank] == (unsigned short)threadIdx.x) {
-              acc[rank] = __dadd_rn(acc[rank], prod);
-              pending = false;
-            }
-          }
-        } else {
-          // ordered commit: the distinct segments of this step, in order, one barrier each.
-          // Lanes 0..NW-1 of every warp look at the step's slots (one per warp).
-          const int sl = s * NW + lane;
-          const bool valid = lane < NW && sl < nslots;
-          const int sv = valid ? (single ? 0 : (int)sm.eslot[sl]) : -1;
-          const int pv = __shfl_up_sync(FULL, sv, 1);
-          const unsigned starts = __ballot_sync(FULL, valid && (lane == 0 || sv != pv));
-          const int nrounds = __popc(starts);
-          const int my_round = __popc(starts & ((2u << warp) - 1u)) - 1;
-          const int e_first = __shfl_sync(FULL, sv, 0);
-          const int e_last = __shfl_sync(FULL, sv, __popc(__ballot_sync(FULL, valid)) - 1);
-          for (int r = 0; r < nrounds; ++r) {
-            if (r > 0 || e_first != e_prev) __syncthreads();  // the previous segment is complete
-            if (r == my_round && c >= 0) acc[rank] = __dadd_rn(acc[rank], prod);
-          }
-          e_prev = e_last;
-        }
-        sub(5);
-      };
-      int e0, e1, e2;
-      issue(0, 0, e0);
-      issue(1, 1, e1);
-      issue(2, 2, e2);
-      for (int s = 0; s < nsteps; s += 3) {
-        consume(s, 0, e0);
-        issue(s + 3, 0, e0);
-        sub(6);
-        if (s + 1 < nsteps) { consume(s + 1, 1, e1); issue(s + 4, 1, e1); }
-        if (s + 2 < nsteps) { consume(s + 2, 2, e2); issue(s + 5, 2, e2); }
-      }
-      // (a segment walked alone may be longer than the table: all its slots belong to it)
-      b0 += nb;
-      e_prev = -1;  // segment numbers restart with the next batch: force a barrier first
-      __syncthreads();
-      lap(2);
-    }
-    // ---- the next item: descriptor parked, its window and A entries requested from L2
-    if (tn < nitems) {
-      if (threadIdx.x < 12) sm.next[threadIdx.x] = nx;
-      if (warp == 0) {
-        const int nW = __shfl_sync(FULL, nx, 2), nnA = __shfl_sync(FULL, nx, 10);
-        const long long nbm = ((long long)__shfl_sync(FULL, nx, 9) << 32) | (unsigned)__shfl_sync(FULL, nx, 8);
-        const long long na0 = ((long long)__shfl_sync(FULL, nx, 5) << 32) | (unsigned)__shfl_sync(FULL, nx, 4);
+      const int desc = field(dv, 0), cnt = field(dv, 1), W = field(dv, 2), c_lo = field(dv, 3);
+      const long long a0 = field64(dv, 4), ob = field64(dv, 6), bmoff = field64(dv, 8);
+      const int nA = field(dv, 10);
+      if (t + 1 < t1) {
+        // the next item of this worker: its window and its A entries requested from L2 now
+        const int nW = field(dv, 16 + 2), nnA = field(dv, 16 + 10);
+        const long long nbm = field64(dv, 16 + 8), na0 = field64(dv, 16 + 4);
         for (int w = lane * 16; w < nW; w += 32 * 16)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(bm_store + nbm + w));
-        for (int k = lane * 32; k < min(nnA, BT); k += 32 * 32) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(Acol + na0 + k));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(Aval + na0 + k));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(Aval + na0 + k + 16));
+        if (lane * 32 < nnA) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Acol + na0 + lane * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Aval + na0 + lane * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Aval + na0 + lane * 32 + 16));
         }
       }
-    }
-    // ---- flush
-    if (on_chip) {
-      for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(Cval + ob + k, acc[k], pol_out);
-      __syncthreads();
-      int* cols = reinterpret_cast<int*>(pool);  // the accumulators' space, now free
-      for (int w = threadIdx.x; w < 2 * W; w += BT) {
+      const int r0 = desc & 255, r1 = (desc >> 8) & 255, mode = desc >> 16;
+      const bool on_chip = mode != ITEM_RED;
+      const unsigned long long* src = bm_store + bmoff;
+      // MULTI: the item's columns are walked in pieces [sw0, sw1) of its window, each piece's
+      // accumulators fitting the pool (16-word steps: 1024 columns can always be held)
+      int sw0 = 0;
+      long long ob_cur = ob;
+      do {
+      int sw1 = W, scnt = cnt;
+      if (mode == ITEM_MULTI) {
+        scnt = 0;
+        sw1 = sw0;
+        while (sw1 < W) {
+          const int nwb = min(16, W - sw1);
+          const int blk = warp_sum_int(lane < nwb ? __popcll(ldg_hint(src + sw1 + lane, pol_bm)) : 0);
+          if (sw1 > sw0 && 8 * (scnt + blk) + 16 * (sw1 - sw0 + nwb) > pool_bytes - 16) break;
+          scnt += blk;
+          sw1 += nwb;
+        }
+      }
+      const int SW = sw1 - sw0;                 // words of this piece
+      const int sc_lo = c_lo + 64 * sw0, sc_hi = c_lo + 64 * sw1;
+      double* acc = reinterpret_cast<double*>(pool);
+      uint2* pk = reinterpret_cast<uint2*>(pool + (on_chip ? (((size_t)scnt * 8 + 15) & ~(size_t)15) : 0));
+      double* gacc = Cval + ob_cur;
+      // ---- window.  Pass 1: every word fetched with independent loads (one round trip for the
+      // whole window), raw bits parked in the pool; the accumulators are zeroed in its shadow.
+      {
+#pragma unroll 4
+        for (int w = lane; w < SW; w += 32) {
+          const unsigned long long x = ldg_hint(src + sw0 + w, pol_bm);
+          pk[2 * w].x = (unsigned)x;
+          pk[2 * w + 1].x = (unsigned)(x >> 32);
+        }
+        if (on_chip) {
+          for (int k = lane; k < scnt; k += 32) acc[k] = 0.0;
+        } else {
+          for (int k = lane; k < scnt; k += 32) stg_hint(gacc + k, 0.0, pol_acc);
+        }
+        __syncwarp();
+        // pass 2: rank prefix, 32 words (64 packed entries) per step
+        int run = 0;
+        for (int w0 = 0; w0 < SW; w0 += 32) {
+          const int w = w0 + lane;
+          unsigned lo32 = 0, hi32 = 0;
+          if (w < SW) { lo32 = pk[2 * w].x; hi32 = pk[2 * w + 1].x; }
+          const int cl = __popc(lo32), c = cl + __popc(hi32);
+          int inc = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += y;
+          }
+          if (w < SW) {
+            const unsigned ex = (unsigned)(run + inc - c);
+            pk[2 * w].y = ex;
+            pk[2 * w + 1].y = ex + cl;
+          }
+          run += __shfl_sync(FULL, inc, 31);
+        }
+        __syncwarp();
+      }
+      // ---- walk
+      for (long long b0 = 0; b0 < nA; b0 += 32) {
+        long long seg_s = 0;
+        int seg_l = 0;
+        double seg_a = 0.0;
+        if (b0 + lane < nA) {
+          const int j = __ldg(Acol + a0 + b0 + lane);
+          seg_a = __ldg(Aval + a0 + b0 + lane);
+          const long long rp = __ldg(Brp + j);
+          const unsigned* sp = split + (size_t)j * R;
+          const long long o0 = (r0 == 0) ? 0 : (long long)__ldg(sp + r0 - 1);
+          const long long o1 = (r1 == R) ? (__ldg(Brp + j + 1) - rp) : (long long)__ldg(sp + r1 - 1);
+          seg_s = rp + o0;
+          seg_l = (int)(o1 - o0);
+        }
+        unsigned todo = __ballot_sync(FULL, seg_l > 0);
+        long long cur_s = 0;
+        int rem = 0;
+        double cur_a = 0.0;
+        while (todo || rem) {
+          // up to UNIT_DEPTH chunks (<= 32 consecutive products of one segment each), in order:
+          // all their loads first, then all their rank look-ups, then the updates one by one
+          int cc[UNIT_DEPTH], rk[UNIT_DEPTH];
+          double cv[UNIT_DEPTH], ca[UNIT_DEPTH];
+          unsigned fresh = 0;  // bit u: chunk u starts a new segment (its updates wait for the previous one's)
+#pragma unroll
+          for (int u = 0; u < UNIT_DEPTH; ++u) {
+            cc[u] = -1;
+            cv[u] = 0.0;
+            ca[u] = 0.0;
+            if (rem == 0 && todo) {
+              const int e = __ffs((int)todo) - 1;
+              todo &= todo - 1;
+              cur_s = shfl64(seg_s, e);
+              rem = __shfl_sync(FULL, seg_l, e);
+              cur_a = shfld(seg_a, e);
+              fresh |= 1u << u;
+            }
+            if (rem > 0) {
+              if (lane < rem) {
+                cc[u] = ldg_hint(Bcol + cur_s + lane, pol_b);
+                cv[u] = ldg_hint(Bval + cur_s + lane, pol_b);
+                // (a piece of a MULTI item sees the whole segment and takes its own columns)
+                if (mode == ITEM_MULTI && (cc[u] < sc_lo || cc[u] >= sc_hi)) cc[u] = -1;
+              }
+              ca[u] = cur_a;
+              const int n = min(rem, 32);
+              cur_s += n;
+              rem -= n;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNIT_DEPTH; ++u) {
+            rk[u] = 0;
+            if (cc[u] >= 0) {
+              const uint2 p = pk[(cc[u] - sc_lo) >> 5];
+              rk[u] = (int)p.y + __popc(p.x & ((1u << (cc[u] & 31)) - 1u));
+              cv[u] = __dmul_rn(ca[u], cv[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNIT_DEPTH; ++u) {
+            // chunks of one segment touch distinct entries: only a new segment has to wait
+            if ((fresh >> u) & 1u) __syncwarp();
+            if (cc[u] >= 0) {
+              if (on_chip) acc[rk[u]] = __dadd_rn(acc[rk[u]], cv[u]);
+              else red_add_hint(gacc + rk[u], cv[u], pol_acc);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // ---- flush: values, then the columns through the pool
+      if (on_chip)
+        for (int k = lane; k < scnt; k += 32) stg_hint(Cval + ob_cur + k, acc[k], pol_out);
+      __syncwarp();
+      const bool stage = on_chip || (size_t)SW * 16 + (size_t)scnt * 4 <= (size_t)pool_bytes;
+      int* cols = on_chip ? reinterpret_cast<int*>(pool) : reinterpret_cast<int*>(pool + (size_t)SW * 16);
+      for (int w = lane; w < 2 * SW; w += 32) {
         const uint2 p = pk[w];
         unsigned x = p.x;
         int pos = (int)p.y;
-        const int cb = c_lo + w * 32;
+        const int cb = sc_lo + w * 32;
         while (x) {
           const int b = __ffs((int)x) - 1;
           x &= x - 1;
-          cols[pos++] = cb + b;
+          if (stage) cols[pos++] = cb + b;
+          else stg_hint(Ccol + ob_cur + pos++, cb + b, pol_out);
         }
       }
-      __syncthreads();
-      for (int k = threadIdx.x; k < cnt; k += BT) stg_hint(Ccol + ob + k, cols[k], pol_out);
-    } else {
-      for (int w = threadIdx.x; w < 2 * W; w += BT) {
-        const uint2 p = pk[w];
-        unsigned x = p.x;
-        int pos = (int)p.y;
-        const int cb = c_lo + w * 32;
-        while (x) {
-          const int b = __ffs((int)x) - 1;
-          x &= x - 1;
-          stg_hint(Ccol + ob + pos++, cb + b, pol_out);
-        }
-      }
+      __syncwarp();
+      if (stage)
+        for (int k = lane; k < scnt; k += 32) stg_hint(Ccol + ob_cur + k, cols[k], pol_out);
+      __syncwarp();
+      ob_cur += scnt;
+      sw0 = sw1;
+      } while (sw0 < W);
     }
-    lap(3);
   }
-  if (prof && threadIdx.x == 0)
-    for (int k = 0; k < 8; ++k) atomicAdd(prof + k, (unsigned long long)pcyc[k]);
 }

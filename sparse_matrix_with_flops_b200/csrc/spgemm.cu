@@ -920,8 +920,8 @@ k_sym_bitmap(const int* __restrict__ list, int count, int row_lo,
   __shared__ int s_pc[BT / 32][PARTS_WHOLE];
   __shared__ int s_idx;
   // output columns per static column range (ranges.cuh), for the rows whose bitmap is stored
-  __shared__ int s_rc[64];
-  if (threadIdx.x < 64) s_rc[threadIdx.x] = 0;
+  __shared__ int s_rc[128];
+  if (threadIdx.x < 128) s_rc[threadIdx.x] = 0;
   WalkSmem<BT>& ws = *reinterpret_cast<WalkSmem<BT>*>(smem_raw);
   unsigned long long* bm = SMEM_BM ? (unsigned long long*)(smem_raw + sizeof(WalkSmem<BT>))
                                    : gscratch + (size_t)blockIdx.x * nw64;
@@ -1792,8 +1792,6 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_TEAM_MAX")) t->team_max = std::max(1, atoi(e));
   if (const char* e = getenv("B200_RANGES")) t->ranges = atoi(e);
   if (const char* e = getenv("B200_ARENA_ENTRIES")) t->arena_entries = atoll(e);
-  if (const char* e = getenv("B200_CHUNK_MIN")) t->chunk_min = atoi(e);
-  t->no_tag = flag("B200_NO_TAG");
   t->deterministic = flag("B200_DETERMINISTIC");
   if (t->deterministic) t->on_chip = true;
 }
@@ -2024,10 +2022,11 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   // (it counts the output columns per static range) and the part kernel as its fallback.
   const int RNG = c.tun.ranges;
   const bool want_ranges = use_parts && sym_smem && RNG >= 2 && RNG <= RANGES_MAX && c.tun.on_chip;
-  constexpr int ITEM_BT = 512, ITEM_CTAS = 2;
-  const size_t item_dyn = (c.smem_optin + 1024) / ITEM_CTAS - 1024 - 512;
-  const size_t item_fixed = (sizeof(ItemSmem<ITEM_BT>) + 15) & ~(size_t)15;
-  const int item_pool = (int)(item_dyn - item_fixed) - 16;
+  // four 4-warp CTAs per SM, every warp an independent worker with its own pool
+  constexpr int UNIT_CTAS = 4;
+  const int unit_pool = (int)((((c.smem_optin + 1024) / UNIT_CTAS - 1024) / UNIT_WARPS) & ~(size_t)15);
+  const size_t unit_dyn = (size_t)unit_pool * UNIT_WARPS;
+  const int item_pool = unit_pool - 16;
 
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
@@ -2206,8 +2205,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(T.alloc(&d_rcnt, (size_t)store_rows * RNG));
       const int hgrid = (int)std::min<long long>((Bs.nnz + 255) / 256, (long long)c.sm_count * 16);
       k_col_hist<<<hgrid, 256, 0, st>>>(Bs.col, Bs.nnz, d_hist);
-      // a range is at most a quarter of the pool wide, so that any single range fits as a window
-      const int wcap = std::max(1, item_pool / 16 / 4);
+      // a range is at most half a pool wide, so that any single range fits as a window
+      const int wcap = std::max(1, item_pool / 16 / 2);
       k_make_ranges<<<1, 1024, 0, st>>>(d_hist, nw64, Bs.nnz, RNG, wcap, d_rw, d_wr);
       k_range_split<<<(unsigned)(((long long)Bs.rows * 32 + 255) / 256), 256, 0, st>>>(
           Bs.rowptr, Bs.col, Bs.rows, RNG, d_rw, d_split);
@@ -2427,11 +2426,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         B200_CUDA(cudaMemsetAsync(d_nitems + nbig_num, 0, sizeof(int), st));
         B200_CUDA(cudaMemsetAsync(d_fbcnt, 0, sizeof(int), st));
         const int pgridp = (nbig_num + 255) / 256;
-        const int chunk_min = c.tun.deterministic ? 0 : c.tun.chunk_min;
-        const int short_mode = c.tun.no_tag ? ITEM_RED : ITEM_TAG;
         k_plan_items<<<pgridp, 256, 0, st>>>(lst, nbig_num, d_bmslot, d_rcnt, d_rw, RNG, item_pool,
-                                             chunk_min, short_mode, nw64, d_flops, A.rowptr, row_lo,
-                                             d_urp, d_nitems, nullptr, nullptr, d_fb, d_fbcnt);
+                                             nw64, c.tun.deterministic ? 1 : 0, A.rowptr, row_lo, d_urp,
+                                             d_nitems, nullptr, nullptr, d_fb, d_fbcnt);
         {
           void* tmp = nullptr;
           size_t tb = 0;
@@ -2449,23 +2446,16 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
           RangeItem* d_items = nullptr;
           B200_CUDA(T.alloc(&d_items, (size_t)h_items));
           k_plan_items<<<pgridp, 256, 0, st>>>(lst, nbig_num, d_bmslot, d_rcnt, d_rw, RNG, item_pool,
-                                               chunk_min, short_mode, nw64, d_flops, A.rowptr, row_lo,
-                                               d_urp, d_nitems, d_itoff, d_items, d_fb, d_fbcnt);
-          if ((rc = set_smem(k_num_items<ITEM_BT, ITEM_CTAS>, item_dyn))) return rc;
-          const int igrid = std::min(h_items, ITEM_CTAS * c.sm_count);
-          k_num_items<ITEM_BT, ITEM_CTAS><<<igrid, ITEM_BT, item_dyn, st>>>(
-              d_items, h_items, RNG, A.col, A.val, Bs.rowptr, Bs.col, Bs.val, d_split, d_bmstore,
-              out_col, out_val, l2m, d_prof);
+                                               nw64, c.tun.deterministic ? 1 : 0, A.rowptr, row_lo, d_urp,
+                                               d_nitems, d_itoff, d_items, d_fb, d_fbcnt);
+          if ((rc = set_smem(k_num_units<UNIT_WARPS>, unit_dyn))) return rc;
+          const int igrid = std::min((h_items + UNIT_WARPS - 1) / UNIT_WARPS, UNIT_CTAS * c.sm_count);
+          k_num_units<UNIT_WARPS><<<igrid, UNIT_WARPS * 32, unit_dyn, st>>>(
+              d_items, h_items, RNG, unit_pool, A.col, A.val, Bs.rowptr, Bs.col, Bs.val, d_split,
+              d_bmstore, out_col, out_val, d_work + 3, l2m);
           launches += 2;
-          if (d_prof) {
-            unsigned long long h[8];
-            B200_CUDA(d2h_small(h, d_prof, sizeof h, st));
-            B200_CUDA(sync_fetch(st));
-            B200_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
-            fprintf(stderr, "[b200 prof] k_num_items: %d items (%d fallback rows), Mcycles/CTA: window %.2f zero %.2f "
-                    "table %.2f walk %.2f flush %.2f | walk: wait+rank %.2f rounds %.2f issue(1/3) %.2f (grid %d)\n", h_items, h_fb, h[0] / 1e6 / igrid,
-                    0.0, h[1] / 1e6 / igrid, h[2] / 1e6 / igrid, h[3] / 1e6 / igrid, h[4] / 1e6 / igrid, h[5] / 1e6 / igrid, h[6] / 1e6 / igrid, igrid);
-          }
+          if (c.tun.prof) fprintf(stderr, "[b200 prof] k_num_units: %d items, %d fallback rows, pool %d B per warp\n",
+                                  h_items, h_fb, unit_pool);
         }
         range_items = h_items;
         plist = d_fb;

@@ -157,17 +157,16 @@ HEAVY = [
     ("rmat13_sym", lambda s: s.synth_rmat(13, 16, 3, True)),           # hub rows with > 10^3 A entries
     ("planted_dense", lambda s: s.synth_planted(3000, 3, 60, 4, 7)),   # ~1000-column rows, ~16 K products
 ]
-# the numeric pass of the heavy rows: on-chip range items (default: mode chosen per item), every
-# item forced to commit in A-entry order / by tag arbitration / with global RED accumulators,
-# few wide / many narrow ranges, and the part kernel alone
+# the numeric pass of the heavy rows: the part kernel (default) and the on-chip range items with
+# few wide / many narrow column ranges
 HEAVY_MODES = [
     ("default", {}),                                   # part kernel: global fp64 RED
-    ("on_chip", {"B200_ON_CHIP": 1}),                  # range items, mode chosen per item
-    ("all_ordered", {"B200_DETERMINISTIC": 1}),
-    ("all_tag", {"B200_ON_CHIP": 1, "B200_CHUNK_MIN": 1000000000}),
-    ("all_red", {"B200_ON_CHIP": 1, "B200_CHUNK_MIN": 1000000000, "B200_NO_TAG": 1}),
-    ("ranges4_tag", {"B200_ON_CHIP": 1, "B200_RANGES": 4, "B200_CHUNK_MIN": 1000000000}),
-    ("ranges7_ordered", {"B200_ON_CHIP": 1, "B200_RANGES": 7, "B200_CHUNK_MIN": 0}),
+    ("on_chip", {"B200_ON_CHIP": 1}),                  # range items, one warp each, A-entry order
+    ("deterministic", {"B200_DETERMINISTIC": 1}),
+    ("ranges4", {"B200_ON_CHIP": 1, "B200_RANGES": 4}),   # few wide ranges: items that overflow -> RED
+    ("ranges7", {"B200_ON_CHIP": 1, "B200_RANGES": 7}),
+    ("ranges128", {"B200_ON_CHIP": 1, "B200_RANGES": 128}),
+    ("ranges2_deterministic", {"B200_DETERMINISTIC": 1, "B200_RANGES": 2}),  # overflow -> column passes
 ]
 
 
@@ -192,13 +191,14 @@ def test_heavy_row_paths(gpu, name, make, mode, opts, b200_options):
     ol.assert_same(M_of(step), want1, TOL, name + " " + mode + " rMCL step")
 
 
+@pytest.mark.parametrize("ranges", [128, 2])
 @pytest.mark.parametrize("name,make", HEAVY)
-def test_on_chip_items_are_bit_identical(gpu, name, make, b200_options):
+def test_on_chip_items_are_bit_identical(gpu, name, make, ranges, b200_options):
     """An ordered on-chip item commits the B-row segments in A-entry order with separately rounded
     multiply and add (indexProcessCRowI's order): with B200_DETERMINISTIC every item runs that
     way and the whole product equals the reference's bit for bit — heavy rows included — and is
     the same on every run."""
-    b200_options(B200_DETERMINISTIC=1)
+    b200_options(B200_DETERMINISTIC=1, B200_RANGES=ranges)   # 2 ranges: they overflow a warp's pool
     A = make(gpu)
     got, want = gpu_spgemm(gpu, A, A), want_spgemm(A, A)
     assert np.array_equal(got.I, want.I) and np.array_equal(got.J, want.J)
