@@ -350,19 +350,23 @@ class COO {
     fclose(f);
     return 0;
   }
-  // sort by (row, col) and drop repeated (row, col) pairs, keeping the first
-  // (nlibs/COO.cc:237-266); returns the number of entries removed
+  // COO::orderedAndDuplicatesRemoving (nlibs/COO.cc:237-266): sort by (row, col), ADD the values
+  // of repeated (row, col) pairs into one entry, return the NEW nnz.  (The reference sorts with
+  // an unstable std::sort, so for a pair given three or more times its rounding depends on the
+  // order that sort leaves; here the values are added in input order.)
   int orderedAndDuplicatesRemoving() {
     makeOrdered();
     int top = 0;
     for (int e = 0; e < nnz; ++e) {
-      if (top && cooRowIndex[e] == cooRowIndex[top - 1] && cooColIndex[e] == cooColIndex[top - 1]) continue;
+      if (top && cooRowIndex[e] == cooRowIndex[top - 1] && cooColIndex[e] == cooColIndex[top - 1]) {
+        cooVal[top - 1] += cooVal[e];
+        continue;
+      }
       cooRowIndex[top] = cooRowIndex[e]; cooColIndex[top] = cooColIndex[e]; cooVal[top] = cooVal[e];
       ++top;
     }
-    const int removed = nnz - top;
     nnz = top;
-    return removed;
+    return nnz;
   }
   // one (i,i,1.0) entry for every vertex without a diagonal entry; input must be duplicate free
   // (SURVEY.md §8c input hazards)
@@ -382,7 +386,8 @@ class COO {
     std::vector<int> perm(nnz);
     std::iota(perm.begin(), perm.end(), 0);
     const int* r = cooRowIndex; const int* c = cooColIndex;
-    std::sort(perm.begin(), perm.end(), [r, c](int x, int y) { return r[x] != r[y] ? r[x] < r[y] : c[x] < c[y]; });
+    // stable: entries with the same (row, col) keep their input order (the device build does too)
+    std::stable_sort(perm.begin(), perm.end(), [r, c](int x, int y) { return r[x] != r[y] ? r[x] < r[y] : c[x] < c[y]; });
     std::vector<int> rr(nnz), cc(nnz);
     std::vector<QValue> vv(nnz);
     for (int e = 0; e < nnz; ++e) { rr[e] = cooRowIndex[perm[e]]; cc[e] = cooColIndex[perm[e]]; vv[e] = cooVal[perm[e]]; }

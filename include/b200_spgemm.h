@@ -156,9 +156,11 @@ int b200_csr_free(b200_csr_t h);
  * on the device.  Replaces COO::addSelfLoopIfNeeded (nlibs/COO.cc:160-188), COO::makeOrdered +
  * COO::toCSR (COO.cc:222-235), orderedAndDuplicatesRemoving (COO.cc:237-266) and
  * CSR::averAndNormRowQValue (nlibs/CSR.cc:88-95); B200_COO_SELF_LOOPS | B200_COO_NORMALISE is
- * rmclInit (nlibs/qrmcl.cc:126-134).  Entries come out ordered by (row, column); of repeated
- * (row, column) pairs the first in input order stays when B200_COO_DEDUP is set (without it they
- * all stay, which the multiplication entry points do not accept: SURVEY.md §8c input hazards).
+ * rmclInit (nlibs/qrmcl.cc:126-134).  Entries come out ordered by (row, column); with
+ * B200_COO_DEDUP repeated (row, column) pairs become ONE entry whose value is the sum of theirs,
+ * added in input order, as orderedAndDuplicatesRemoving does (COO.cc:246-248; with
+ * B200_COO_NORMALISE the value is 1 / rowcount anyway) — without the flag they all stay, which
+ * the multiplication entry points do not accept (SURVEY.md §8c input hazards).
  * Indices outside the matrix are an error. */
 #define B200_COO_DEDUP 1
 #define B200_COO_SELF_LOOPS 2

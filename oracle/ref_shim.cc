@@ -182,6 +182,21 @@ void ref_pcsr_split(int* I, int* J, double* V, int rows, int cols, int c, int* b
   P.dispose();
 }
 
+// COO::orderedAndDuplicatesRemoving (nlibs/COO.cc:237-266) on an in-memory COO: entries sorted
+// by (row, col), the values of repeated pairs SUMMED, returns the new nnz (also the method's
+// return value, in *ret).  Outputs are copies of the first new-nnz entries.
+int ref_coo_dedup(const int* er, const int* ec, const double* ev, int nedges, int rows, int cols,
+                  int* r_out, int* c_out, double* v_out, int* ret) {
+  COO coo(ev, ec, er, rows, cols, nedges);   // (values, colIndex, rowIndex, ...) deep copy, COO.cc:24-35
+  *ret = coo.orderedAndDuplicatesRemoving();
+  const int nn = coo.nnz;
+  memcpy(r_out, coo.cooRowIndex, sizeof(int) * nn);
+  memcpy(c_out, coo.cooColIndex, sizeof(int) * nn);
+  memcpy(v_out, coo.cooVal, sizeof(double) * nn);
+  coo.dispose();
+  return nn;
+}
+
 void ref_free(void* p) { free(p); }
 
 }  // extern "C"

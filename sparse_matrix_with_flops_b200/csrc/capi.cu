@@ -48,11 +48,6 @@ __global__ void k_i64_to_i32_rebased(const int64_t* __restrict__ in, int* __rest
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int)(in[i] - in[0]);
 }
-__global__ void k_rebase_rowptr(const int64_t* __restrict__ in, int64_t* __restrict__ out,
-                                long long n, long long add) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] - in[0] + add;
-}
 // argmax per row, ties -> smallest column; one thread per row (rows of a converged Mt are tiny)
 __global__ void k_row_argmax(const int64_t* __restrict__ rp, const int* __restrict__ col,
                              const double* __restrict__ val, int m, int* __restrict__ lab) {
@@ -408,24 +403,24 @@ int upload(const int* I, const int* J, const double* V, int rows, int cols, int 
   }
   DevCSR d;
   d.rows = rows; d.cols = cols; d.nnz = nnz;
+  Temps T;  // every array is freed on an error path; the three result arrays are kept at the end
   int* tmp = nullptr;
-  B200_CUDA(dalloc(&tmp, (size_t)rows + 1));
-  B200_CUDA(dalloc(&d.rowptr, (size_t)rows + 1));
-  B200_CUDA(dalloc(&d.col, (size_t)nnz));
-  B200_CUDA(dalloc(&d.val, (size_t)nnz));
+  B200_CUDA(T.alloc(&tmp, (size_t)rows + 1));
+  B200_CUDA(T.alloc(&d.rowptr, (size_t)rows + 1));
+  B200_CUDA(T.alloc(&d.col, (size_t)nnz));
+  B200_CUDA(T.alloc(&d.val, (size_t)nnz));
   B200_CUDA(cudaMemcpyAsync(tmp, I, ((size_t)rows + 1) * sizeof(int), cudaMemcpyHostToDevice, c.stream));
   k_i32_to_i64<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, c.stream>>>(tmp, d.rowptr, rows + 1);
-  dfree(tmp);
   B200_CUDA(cudaStreamSynchronize(c.stream));
   if (nnz) {
     int rc = h2d_staged(d.col, J, (size_t)nnz * sizeof(int));
     if (!rc) rc = h2d_staged(d.val, V, (size_t)nnz * sizeof(double));
-    if (rc) { dfree(d.rowptr); dfree(d.col); dfree(d.val); return rc; }
+    if (rc) return rc;
   }
-  {
-    int rc = check_sorted_device(&d);
-    if (rc) { dfree(d.rowptr); dfree(d.col); dfree(d.val); return rc; }
-  }
+  // sorted rows? and: is it a CSR at all (a bad index must not become an out-of-bounds read)
+  const int rc = check_sorted_device(&d, true);
+  if (rc) return rc;
+  T.keep(d.rowptr); T.keep(d.col); T.keep(d.val);
   *out = d;
   return B200_OK;
 }
@@ -782,15 +777,16 @@ int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix) {
   B200_REQUIRE_INIT();
   int rc = check_mul(A, B, 0, A ? A->d.rows : 0);
   if (rc) return rc;
+  if (!prefix) { set_error("null output"); return B200_ERR_BAD_ARG; }
   Ctx& c = ctx();
   const int m = A->d.rows;
+  Temps T;
   int64_t* d_prefix = nullptr;
-  B200_CUDA(dalloc(&d_prefix, (size_t)m + 1));
+  B200_CUDA(T.alloc(&d_prefix, (size_t)m + 1));
   rc = flops_prefix_device(A->d, B->d, 0, m, d_prefix);
   if (rc) return rc;
   B200_CUDA(cudaMemcpyAsync(prefix, d_prefix, ((size_t)m + 1) * sizeof(long long),
                             cudaMemcpyDeviceToHost, c.stream));
-  dfree(d_prefix);
   B200_CUDA(cudaStreamSynchronize(c.stream));
   return B200_OK;
 }
@@ -831,33 +827,20 @@ int b200_csr_row_argmax(b200_csr_t h, int* labels) {
 int b200_csr_concat_rows(const b200_csr_t* blocks, int nblocks, b200_csr_t* out) {
   B200_REQUIRE_INIT();
   if (!blocks || nblocks < 1 || !out) { set_error("bad argument"); return B200_ERR_BAD_ARG; }
-  Ctx& c = ctx();
-  long long rows = 0, nnz = 0;
+  long long rows = 0;
+  std::vector<DevCSR> v;
   for (int b = 0; b < nblocks; ++b) {
     if (!blocks[b] || blocks[b]->d.cols != blocks[0]->d.cols) { set_error("blocks disagree on cols"); return B200_ERR_BAD_ARG; }
     rows += blocks[b]->d.rows;
-    nnz += blocks[b]->d.nnz;
+    v.push_back(blocks[b]->d);
   }
   if (rows > INT_MAX) { set_error("too many rows"); return B200_ERR_INT32_OVERFLOW; }
+  DevCSR d;
+  const int rc = concat_rows_device(v, blocks[0]->d.cols, &d);   // frees its arrays on an error path
+  if (rc) return rc;
+  B200_CUDA(cudaStreamSynchronize(ctx().stream));
   b200_csr* h = new b200_csr();
-  DevCSR& d = h->d;
-  d.rows = (int)rows; d.cols = blocks[0]->d.cols; d.nnz = nnz;
-  B200_CUDA(dalloc(&d.rowptr, (size_t)rows + 1));
-  B200_CUDA(dalloc(&d.col, (size_t)nnz));
-  B200_CUDA(dalloc(&d.val, (size_t)nnz));
-  long long r0 = 0, z0 = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    const DevCSR& s = blocks[b]->d;
-    k_rebase_rowptr<<<(unsigned)((s.rows + 1 + 255) / 256), 256, 0, c.stream>>>(s.rowptr, d.rowptr + r0, s.rows + 1, z0);
-    if (s.nnz) {
-      B200_CUDA(cudaMemcpyAsync(d.col + z0, s.col, (size_t)s.nnz * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
-      B200_CUDA(cudaMemcpyAsync(d.val + z0, s.val, (size_t)s.nnz * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-    }
-    r0 += s.rows;
-    z0 += s.nnz;
-  }
-  B200_CUDA(cudaStreamSynchronize(c.stream));
-  B200_CUDA(cudaGetLastError());
+  h->d = d;
   *out = h;
   return B200_OK;
 }

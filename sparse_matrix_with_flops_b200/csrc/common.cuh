@@ -184,7 +184,7 @@ int equal_partition_device(const int64_t* d_prefix, int n, int nparts, int* h_en
 // CSR::makeOrdered on the device (spgemm.cu)
 int sort_rows_device(DevCSR* d);
 // sets d->sorted_rows (spgemm.cu)
-int check_sorted_device(DevCSR* d);
+int check_sorted_device(DevCSR* d, bool validate = false);
 
 // flops prefix on device (spgemm.cu)
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,

@@ -2,7 +2,7 @@
 // hot path).  Restates, for an edge list already in device memory:
 //   COO::addSelfLoopIfNeeded        nlibs/COO.cc:160-188  (one (i,i,1.0) per vertex without a diagonal)
 //   COO::makeOrdered / toCSR        nlibs/COO.cc:222-235  (entries ordered by (row, col), row offsets)
-//   orderedAndDuplicatesRemoving    nlibs/COO.cc:237-266  (repeated (row, col) pairs: the first stays)
+//   orderedAndDuplicatesRemoving    nlibs/COO.cc:237-266  (repeated (row, col) pairs: ONE entry, values added)
 //   CSR::averAndNormRowQValue       nlibs/CSR.cc:88-95    (every entry of a row = 1 / rowcount)
 // i.e. rmclInit (nlibs/qrmcl.cc:126-134) when self loops + normalisation are asked for.
 //
@@ -55,7 +55,7 @@ __global__ void k_coo_keep(const unsigned long long* __restrict__ key, const uns
 __global__ void k_coo_scatter(const unsigned long long* __restrict__ key, const unsigned* __restrict__ idx,
                               const int* __restrict__ keep, const long long* __restrict__ pos,
                               long long total, long long nnz, const double* __restrict__ val,
-                              const int64_t* __restrict__ rowptr, int normalise,
+                              const int64_t* __restrict__ rowptr, int normalise, int dedup,
                               int* __restrict__ col_out, double* __restrict__ val_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total || !keep[i]) return;
@@ -69,6 +69,14 @@ __global__ void k_coo_scatter(const unsigned long long* __restrict__ key, const 
   } else {
     const long long e = (long long)idx[i];
     v = e < nnz ? (val ? val[e] : 1.0) : 1.0;           // nlibs/COO.cc:183: self loops carry 1.0
+    // orderedAndDuplicatesRemoving (COO.cc:246-248): the entry that stays collects the values of
+    // the repeated pairs behind it, in input order (the sort is stable; a self-loop candidate
+    // behind a real diagonal adds nothing)
+    if (dedup)
+      for (long long q = i + 1; q < total && key[q] == k; ++q) {
+        const long long eq = (long long)idx[q];
+        if (eq < nnz) v += val ? val[eq] : 1.0;
+      }
   }
   val_out[p] = v;
 }
@@ -145,7 +153,7 @@ int coo_build_device(const int* d_row, const int* d_col, const double* d_val, lo
   B200_CUDA(T.alloc(&d.val, (size_t)h_nnz));
   if (total > 0)
     k_coo_scatter<<<grid, 256, 0, st>>>(key2, idx2, keep, pos, total, nnz, d_val, d.rowptr,
-                                       normalise ? 1 : 0, d.col, d.val);
+                                       normalise ? 1 : 0, dedup ? 1 : 0, d.col, d.val);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(sync_fetch(st));
   d.sorted_rows = dedup;   // strictly ascending by construction once repeated pairs are gone

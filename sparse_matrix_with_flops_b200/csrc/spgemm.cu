@@ -1605,15 +1605,28 @@ k_team_sizes(const int* __restrict__ list, int count, int nparts,
   tsize[q] = T;
 }
 
-// every row strictly ascending?  flag[0] is cleared by any violating pair
+// every row strictly ascending?  flag[0] is cleared by any violating pair.  With `validate`
+// the CSR itself is checked too — row offsets start at 0, never decrease, end at nnz; columns lie
+// in [0, cols) — and flag[1] is set by any violation (the reference trusts its inputs; here a bad
+// index would otherwise become an out-of-bounds read in the flops kernel and a sticky CUDA error)
 __global__ void __launch_bounds__(256)
-k_check_sorted(const int64_t* __restrict__ rp, const int* __restrict__ col, int m,
-               int* __restrict__ flag) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+k_check_sorted(const int64_t* __restrict__ rp, const int* __restrict__ col, int m, int cols,
+               long long nnz, int validate, int* __restrict__ flag) {
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (warp >= m) return;
-  bool ok = true;
-  for (int64_t p = rp[warp] + 1 + lane; p < rp[warp + 1]; p += 32) ok &= col[p - 1] < col[p];
-  if (!ok) *flag = 0;
+  int64_t s = rp[warp], e = rp[warp + 1];
+  if (validate) {
+    bool bad = s < 0 || e < s || e > nnz || (warp == 0 && s != 0) || (warp == m - 1 && e != nnz);
+    if (bad) { if (lane == 0) flag[1] = 1; return; }
+  }
+  bool ok = true, inside = true;
+  for (int64_t p = s + lane; p < e; p += 32) {
+    const int c = col[p];
+    if (p > s) ok &= col[p - 1] < c;
+    inside &= (unsigned)c < (unsigned)cols;
+  }
+  if (!ok) flag[0] = 0;
+  if (validate && !inside) flag[1] = 1;
 }
 
 // keys for ordering a bitmap-bin list heaviest first: key[t] = flops[list[t]]
@@ -1884,21 +1897,30 @@ static int sorted_copy_device(const DevCSR& d, int** col2, double** val2) {
   return B200_OK;
 }
 
-int check_sorted_device(DevCSR* d) {
+int check_sorted_device(DevCSR* d, bool validate) {
   Ctx& c = ctx();
   d->sorted_rows = true;
-  if (d->rows == 0 || d->nnz == 0) return B200_OK;
+  if (d->rows == 0) {
+    if (validate && d->nnz != 0) { set_error("bad CSR: entries without rows"); return B200_ERR_BAD_ARG; }
+    return B200_OK;
+  }
+  if (d->nnz == 0 && !validate) return B200_OK;
+  Temps T;
   int* d_flag = nullptr;
-  int h = 1;
+  int h[2] = {1, 0};
   rb_reset();
-  B200_CUDA(dalloc(&d_flag, 1));
-  B200_CUDA(cudaMemcpyAsync(d_flag, &h, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  B200_CUDA(T.alloc(&d_flag, 2));
+  B200_CUDA(cudaMemcpyAsync(d_flag, h, sizeof h, cudaMemcpyHostToDevice, c.stream));
   const long long threads = (long long)d->rows * 32;
-  k_check_sorted<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d->rowptr, d->col, d->rows, d_flag);
-  B200_CUDA(d2h_small(&h, d_flag, sizeof(int), c.stream));
-  dfree(d_flag);
+  k_check_sorted<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d->rowptr, d->col, d->rows, d->cols,
+                                                                         d->nnz, validate ? 1 : 0, d_flag);
+  B200_CUDA(d2h_small(h, d_flag, sizeof h, c.stream));
   B200_CUDA(sync_fetch(c.stream));
-  d->sorted_rows = h != 0;
+  if (h[1]) {
+    set_error("bad CSR: row offsets must start at 0, never decrease and end at nnz; columns must lie in [0, cols)");
+    return B200_ERR_BAD_ARG;
+  }
+  d->sorted_rows = h[0] != 0;
   return B200_OK;
 }
 

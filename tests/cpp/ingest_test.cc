@@ -7,8 +7,22 @@ int main(int argc, char** argv) {
   COO coo;
   coo.readSNAPFile(argv[1], atoi(argv[2]) != 0);
   printf("coo %d %d %d\n", coo.rows, coo.cols, coo.nnz);
-  const int removed = coo.orderedAndDuplicatesRemoving();
-  printf("removed %d\n", removed);
+  const int before = coo.nnz;
+  const int after = coo.orderedAndDuplicatesRemoving();   // returns the NEW nnz (nlibs/COO.cc:265)
+  printf("removed %d\n", before - after);
+  if (argc > 4) {   // dedup check: "r c v" triples on stdin, printed back after the call
+    COO d;
+    d.rows = atoi(argv[4]); d.cols = atoi(argv[5]);
+    int cap = 1 << 16, n = 0;
+    d.cooRowIndex = (int*)malloc(cap * sizeof(int)); d.cooColIndex = (int*)malloc(cap * sizeof(int));
+    d.cooVal = (QValue*)malloc(cap * sizeof(QValue));
+    while (n < cap && scanf("%d %d %lf", &d.cooRowIndex[n], &d.cooColIndex[n], &d.cooVal[n]) == 3) ++n;
+    d.nnz = n;
+    const int ret = d.orderedAndDuplicatesRemoving();
+    printf("dedup %d %d\n", ret, d.nnz);
+    for (int e = 0; e < d.nnz; ++e) printf("d %d %d %.17g\n", d.cooRowIndex[e], d.cooColIndex[e], d.cooVal[e]);
+    d.dispose();
+  }
   for (int e = 0; e < coo.nnz; ++e) printf("e %d %d %.17g\n", coo.cooRowIndex[e], coo.cooColIndex[e], coo.cooVal[e]);
   CSR M = rmclInit(coo);
   printf("csr %d %d %d\n", M.rows, M.cols, M.nnz);

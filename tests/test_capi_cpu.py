@@ -156,6 +156,22 @@ def test_cpp_ingest_matches_reference_golden(golden, tmp_path):
                            "-L" + os.path.join(ROOT, "sparse_matrix_with_flops_b200"), "-lb200spgemm",
                            "-Wl,-rpath," + os.path.join(ROOT, "sparse_matrix_with_flops_b200")])
 
+    # orderedAndDuplicatesRemoving against golden vectors of the unmodified reference
+    # (tests/golden/make_golden_dedup.py): repeated pairs summed, the NEW nnz returned
+    gd = np.load(os.path.join(ROOT, "tests", "golden", "golden_dedup_v1.npz"))
+    for tag in ("w", "t"):
+        text = "".join("%d %d %.17g\n" % t for t in zip(gd[tag + "_in_r"], gd[tag + "_in_c"], gd[tag + "_in_v"]))
+        out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "t2_edges.snap"), "1", "2",
+                              str(gd[tag + "_shape"][0]), str(gd[tag + "_shape"][1])],
+                             input=text, capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        L = [ln.split() for ln in out.stdout.splitlines()]
+        ret, nn = (int(x) for x in [x for x in L if x[0] == "dedup"][0][1:])
+        assert ret == nn == int(gd[tag + "_ret"][0])
+        rows_ = [x for x in L if x[0] == "d"]
+        assert [int(x[1]) for x in rows_] == list(gd[tag + "_out_r"]) and [int(x[2]) for x in rows_] == list(gd[tag + "_out_c"])
+        assert np.array_equal(np.array([float(x[3]) for x in rows_]).view(np.int64), gd[tag + "_out_v"].view(np.int64))
+
     def run(path, trans, c=2):
         out = subprocess.run([exe, path, str(trans), str(c)], capture_output=True, text=True, timeout=60)
         assert out.returncode == 0, out.stderr

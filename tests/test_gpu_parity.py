@@ -234,6 +234,108 @@ def test_rmcl_through_a_bounded_arena(gpu, name, make, b200_options):
     assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
 
 
+def _check_row_blocks(gpu, A, nblocks, picks, what):
+    """C = A*A computed ONCE on the GPU for the whole matrix (so the heavy-row kernels run with the
+    geometry of the full problem), then the chosen flops-balanced row blocks against the checker
+    on the same rows: rowPtr and sorted colInd exact, values within 1e-12 relative."""
+    M = M_of(A)
+    dA = A.toGpuCSR()
+    pre = gpu.flops_prefix(dA, dA)
+    ends = gpu.arrayEqualPartition64(pre, nblocks)
+    dC, st = gpu.gpuSpMMWrapper(dA, dA, want_stats=True)
+    assert st["products"] == int(pre[-1])
+    worst = 0.0
+    for b in picks:
+        lo, hi = int(ends[b]), int(ends[b + 1])
+        got = M_of(dC.toCpuCSR(lo, hi))
+        blk = ol.M(M.I[lo:hi + 1], M.J, M.V, hi - lo, M.cols)
+        want = ol.o_make_ordered(ol.o_spgemm(blk, M))
+        assert np.array_equal(got.I, want.I), "%s block %d: rowPtr" % (what, b)
+        assert np.array_equal(got.J, want.J), "%s block %d: colInd" % (what, b)
+        rel = float(np.max(np.abs(got.V - want.V) / np.abs(want.V))) if want.nnz else 0.0
+        assert rel <= TOL, "%s block %d: relative value error %.3e" % (what, b, rel)
+        worst = max(worst, rel)
+    dC.deviceDispose()
+    dA.deviceDispose()
+    return st, worst
+
+
+def test_full_scale_rmat18_every_row_block(gpu):
+    """R-MAT scale 18 (products 2.9e9, nnz(C) 1.28e9): the whole product, every row block."""
+    A = gpu.synth_rmat(18, 16, 12345, False)
+    st, worst = _check_row_blocks(gpu, A, 3, [0, 1, 2], "rmat18")
+    assert st["nnz_out"] > 1_000_000_000 and st["part_kernel"] == 1
+
+
+def test_headline_config_rmat20_hub_middle_tail_blocks(gpu):
+    """BASELINE.json configs[1] at full size (R-MAT scale 20: products 2.09e10, nnz(C) 9.7e9 =
+    116 GB in HBM, computed exactly as bench.py does): the hub block, a middle block and the
+    tail block of 21 equal-products row blocks against the checker."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 160e9:
+        pytest.skip("needs a 180 GB device")
+    A = gpu.synth_rmat(20, 16, 12345, False)
+    st, worst = _check_row_blocks(gpu, A, 21, [0, 10, 20], "rmat20")
+    assert st["products"] == 20933223103 and st["nnz_out"] == 9700343247
+
+
+def _squares_around(target):
+    """doubles v whose correctly rounded squares are just below, at (when one exists) and just
+    above `target`"""
+    out = {}
+    v0 = np.sqrt(target)
+    v = np.nextafter(v0, 0)
+    for _ in range(8):
+        v = np.nextafter(v, 0)
+    for _ in range(40):
+        sq = v * v
+        key = "below" if sq < target else ("at" if sq == target else "above")
+        if key == "below" or key not in out:
+            out[key] = v          # the largest v below, the first v at / above
+        v = np.nextafter(v, 1)
+    return out
+
+
+@pytest.mark.parametrize("cnt", [200, 1000, 5000])
+def test_rmcl_rows_with_entries_at_the_pruning_threshold(gpu, cnt):
+    """Keep / drop decisions on the threshold itself (arrayThreshPruneNormalize keeps v >= t,
+    nlibs/tools/util.cc:47-69) for hash-bin rows (200 columns) and bitmap-bin rows (1000, 5000):
+    every row's threshold is the 1e-7 floor (computeThreshold, util.cc:4-9), and its inflated
+    entries are the doubles just below, at and just above 1e-7.  Each product entry is
+    0.5 v + 0.5 v — exact in any order — so the structure must equal the checker's exactly."""
+    sq = _squares_around(1.0e-7)
+    vals = [sq["below"], sq["above"]] + ([sq["at"]] if "at" in sq else [])
+    assert sq["below"] ** 2 < 1e-7 <= sq["above"] ** 2
+    rng = np.random.default_rng(cnt)
+    rows_out = 40
+    n = 2 * rows_out + cnt + 50
+    # Mt rows 2k, 2k+1 (k < rows_out) hold the same `cnt` columns and values; Mgt row k = 0.5, 0.5 on them
+    tI, tJ, tV = [0], [], []
+    for k in range(rows_out):
+        cols = np.sort(rng.choice(n, cnt, replace=False)).astype(np.int32)
+        v = rng.choice(vals, cnt)
+        if k % 4 == 1:
+            v[:] = vals[k % len(vals)]           # a row of equal entries
+        for _ in range(2):
+            tJ.append(cols); tV.append(v); tI.append(tI[-1] + cnt)
+    for _ in range(n - 2 * rows_out):
+        tI.append(tI[-1])
+    Mt = gpu.CSR(np.concatenate(tV), np.concatenate(tJ), np.array(tI, dtype=np.int32), n, n)
+    gI = [0]
+    gJ, gV = [], []
+    for k in range(n):
+        if k < rows_out:
+            gJ += [2 * k, 2 * k + 1]; gV += [0.5, 0.5]
+        gI.append(len(gJ))
+    Mg = gpu.CSR(np.array(gV), np.array(gJ, dtype=np.int32), np.array(gI, dtype=np.int32), n, n)
+    want = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(Mg), M_of(Mt)))
+    got = Mg.staticOmpRmclOneStep(Mt)
+    got.makeOrdered()
+    kept = np.diff(want.I)[:rows_out]
+    assert kept.min() < cnt and kept.max() > 0, "the rows must actually prune something"
+    ol.assert_same(M_of(got), want, TOL, "threshold rows, %d columns" % cnt)
+
+
 def test_sharded_loop_two_ranks_nccl():
     """b200_rmcl_iter_sharded on 2 GPUs (NCCL all-gather of the pruned row blocks + chaos) against
     the checker, one process per GPU.  Needs two devices: skipped on a single-GPU box."""
@@ -536,6 +638,18 @@ def test_error_behaviour(gpu):
     assert rc == 1 and b"row range" in lib.b200_last_error()
     with pytest.raises(AssertionError):
         A.flops_spmm(Bad)                                   # the Python mirror asserts like the reference
+    # an array that is not a CSR is refused at upload with BAD_ARG, not turned into an
+    # out-of-bounds read by the first kernel that follows an index (the context stays healthy)
+    one = np.ones(3)
+    for I, J in (([0, 1, 2, 3], [0, 1, 7]),      # column outside [0, cols)
+                 ([0, 1, 2, 3], [0, -1, 2]),     # negative column
+                 ([0, 2, 1, 3], [0, 1, 2]),      # row offsets decrease
+                 ([1, 1, 2, 3], [0, 1, 2]),      # do not start at 0
+                 ([0, 1, 2, 2], [0, 1, 2])):     # do not end at nnz
+        bad = gpu.CSR(one, np.array(J, dtype=np.int32), np.array(I, dtype=np.int32), 3, 5, nnz=3)
+        with pytest.raises(gpu._lib.B200Error) as ei:
+            bad.toGpuCSR()
+        assert ei.value.code == 1 and "bad CSR" in str(ei.value)
     ok = gpu.gpuSpMMWrapper(dA, dA)                         # still works afterwards
     assert ok.nnz > 0
     ok.deviceDispose(); dA.deviceDispose(); dB.deviceDispose()

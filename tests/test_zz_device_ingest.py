@@ -67,9 +67,16 @@ I = np.zeros(rows + 1, np.int32); np.add.at(I, r + 1, 1); I = np.cumsum(I).astyp
 same(smf.cooToGpuCSR(r, c, v, rows, cols, 0), I, c[o], v[o], "toCSR")
 same(smf.cooToGpuCSR(r, c, None, rows, cols, 0), I, c[o], np.ones(m), "toCSR, no values")
 
-# 5. repeated pairs: the first in input order stays (orderedAndDuplicatesRemoving)
-r2 = np.concatenate([r, r[:700]]); c2 = np.concatenate([c, c[:700]]); v2 = np.concatenate([v, -v[:700]])
-same(smf.cooToGpuCSR(r2, c2, v2, rows, cols, smf.COO_DEDUP), I, c[o], v[o], "dedup keeps the first")
+# 5. repeated pairs become one entry holding the SUM of their values (orderedAndDuplicatesRemoving,
+#    nlibs/COO.cc:237-266): golden vectors produced by the unmodified reference
+gd = np.load(os.path.join(ROOT, "tests", "golden", "golden_dedup_v1.npz"))
+for tag in ("w", "t"):
+    gr, gc = (int(x) for x in gd[tag + "_shape"])
+    d = smf.cooToGpuCSR(gd[tag + "_in_r"], gd[tag + "_in_c"], gd[tag + "_in_v"], gr, gc, smf.COO_DEDUP).toCpuCSR()
+    assert d.nnz == int(gd[tag + "_ret"][0]) == len(gd[tag + "_out_v"])
+    Iw = np.zeros(gr + 1, np.int32); np.add.at(Iw, gd[tag + "_out_r"] + 1, 1); Iw = np.cumsum(Iw).astype(np.int32)
+    assert np.array_equal(d.rowPtr, Iw) and np.array_equal(d.colInd, gd[tag + "_out_c"])
+    assert np.array_equal(d.values.view(np.int64), gd[tag + "_out_v"].view(np.int64)), tag + ": summed values"
 
 # 6. self loops without normalisation carry 1.0 (COO.cc:183) and do not double an existing diagonal
 n = 50
