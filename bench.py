@@ -49,8 +49,21 @@ import time
 # OpenMP runtime is loaded.
 _world = int(os.environ.get("WORLD_SIZE", "1"))
 _is_ref = "reference" in sys.argv
-os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // (1 if _is_ref else _world)))
-os.environ.setdefault("OMP_PROC_BIND", "close")   # BASELINE.md §3 / SURVEY.md §8d timing protocol
+try:
+    _cores = sorted(os.sched_getaffinity(0))
+except AttributeError:
+    _cores = list(range(os.cpu_count() or 1))
+_share = max(1, len(_cores) // (1 if _is_ref else _world))
+os.environ["OMP_NUM_THREADS"] = str(_share)
+# BASELINE.md §3 / SURVEY.md §8d timing protocol: OMP_PROC_BIND=close.  With several ranks on one
+# host every rank needs its OWN places: `close` alone binds every process's threads — the
+# thread that launches the kernels included — to the same first cores (measured, round 2, N = 8:
+# 68 ms per step instead of 34, end-to-end 18 s instead of 6).
+os.environ.setdefault("OMP_PROC_BIND", "close")
+if not _is_ref and _world > 1 and "OMP_PLACES" not in os.environ:
+    _lr = int(os.environ.get("LOCAL_RANK", "0"))
+    _mine = _cores[_lr * _share:(_lr + 1) * _share] or _cores
+    os.environ["OMP_PLACES"] = ",".join("{%d}" % c for c in _mine)
 
 import numpy as np
 
@@ -383,9 +396,11 @@ def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches = 0
+    loops_ms = []
     for dT in dTs:
         done, hist, ms_it, counts = loop(dT)
         launches += int(counts[:, 4].sum())
+        loops_ms.append(round(float(ms_it.sum()), 3))
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -412,6 +427,7 @@ def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
                 "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                 "traffic": None, "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
                 "loop_algorithmic_bytes": int(sum(bytes_it)),
+                "loops_ms_rank0": loops_ms,   # sum of the library's per-iteration CUDA-event times, per timed loop
                 "per_iteration": {"ms": [round(float(x), 3) for x in ms_it],
                                   "products": [int(x) for x in counts[:, 0]],
                                   "nnz_new_Mt": [int(x) for x in counts[:, 1]],

@@ -150,7 +150,9 @@ int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_c
     Temps T;  // d_prefix, d_meta: freed on every path
     int64_t* d_prefix = nullptr;
     long long* d_meta = nullptr;  // per rank: {nnz of its block, error code, chaos bits, unpruned nnz, row tiles}
+    long long* d_P = nullptr;
     constexpr int MW = 5;
+    B200_CUDA(T.alloc(&d_P, 1));
     B200_CUDA(T.alloc(&d_prefix, (size_t)n + 1));
     B200_CUDA(T.alloc(&d_meta, (size_t)R * MW));
     B200_CUDA(cudaEventCreate(&ev.e0));
@@ -167,16 +169,24 @@ int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_c
       //    code travels with the block sizes and every rank leaves the loop together.
       CsrGuard blk;
       double ch = 0.0;
-      int lrc = flops_prefix_device(Mgt->d, cur, 0, n, d_prefix);
+      // (with more than one rank the cut balances products + a charge per heavy row, see
+      // k_row_cost; one rank has nothing to balance)
+      int lrc = flops_prefix_device(Mgt->d, cur, 0, n, d_prefix, R > 1 ? c.tun.row_charge : 0, d_P);
       if (!lrc) lrc = equal_partition_device(d_prefix, n, R, ends.data());
       long long P_total = 0;
       if (!lrc && counts_per_iter)
-        B200_CUDA(cudaMemcpyAsync(&P_total, d_prefix + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(&P_total, d_P, sizeof(long long), cudaMemcpyDeviceToHost, st));
       if (!lrc) lrc = rmcl_step_device(Mgt->d, cur, ends[r], ends[r + 1], &blk.d, &ch,
                                        counts_per_iter ? &bst : nullptr);
       long long unpruned = (counts_per_iter && !lrc) ? bst.nnz_unpruned : 0;
       long long tiles = (counts_per_iter && !lrc) ? std::max(1, bst.row_tiles) : 0;
       const long long launches = (counts_per_iter && !lrc) ? bst.launches : 0;
+      // With several ranks every rank would otherwise sort the WHOLE gathered Mt again at the
+      // start of the next step (the bitmap kernels cut B rows at column boundaries): each rank
+      // orders its own block before the exchange instead — 1/R of that work.  (Ascending rows
+      // change the first-touch order the next iteration's hash bins see, i.e. the order of its
+      // row sums: values agree with a 1-rank run to rounding, not bitwise.)
+      if (R > 1 && !lrc && blk.d.nnz > 0 && !blk.d.sorted_rows) lrc = sort_rows_device(&blk.d);
       CsrGuard next;
       if (R == 1) {
         if (lrc) return lrc;
@@ -206,6 +216,7 @@ int b200_rmcl_iter_sharded_stats(int maxIter, double eps, b200_csr_t Mgt, b200_c
           tiles = std::max(tiles, meta[MW * q + 4]);
         }
         next.d.rows = n; next.d.cols = cur.cols; next.d.nnz = off[R];
+        next.d.sorted_rows = true;   // every rank sorted its block
         B200_CUDA(dalloc(&next.d.rowptr, (size_t)n + 1));
         B200_CUDA(dalloc(&next.d.col, (size_t)next.d.nnz));
         B200_CUDA(dalloc(&next.d.val, (size_t)next.d.nnz));

@@ -48,6 +48,8 @@ struct Tunables {
   long long light_p = -1;
   long long team_products = 98304;  // B200_TEAM_P, B200_TEAM_MAX: team sizing of the part kernel
   int team_max = 64;
+  long long row_charge = 32768;  // B200_ROW_CHARGE: products-equivalent cost of a heavy row in the
+                                 // partition of an rMCL step among GPUs (0: equal products, as the reference)
   long long arena_entries = 0;  // B200_ARENA_ENTRIES: products per row tile of an rMCL step (0: from free memory)
   int ranges = 128;     // B200_RANGES: static column ranges of the on-chip numeric pass (2..128)
   bool deterministic = false;  // B200_DETERMINISTIC: B200_ON_CHIP (heavy rows accumulate on chip in
@@ -187,7 +189,10 @@ int sort_rows_device(DevCSR* d);
 int check_sorted_device(DevCSR* d, bool validate = false);
 
 // flops prefix on device (spgemm.cu)
+// row_charge > 0: prefix of the partition COST (products + row_charge per heavy row) instead;
+// d_products (device, may be null) then still receives the plain product total
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,
-                        int64_t* d_prefix /* rows+1 */);
+                        int64_t* d_prefix /* rows+1 */, long long row_charge = 0,
+                        long long* d_products = nullptr);
 
 }  // namespace b200

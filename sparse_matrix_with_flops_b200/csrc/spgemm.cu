@@ -1805,6 +1805,7 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_TEAM_MAX")) t->team_max = std::max(1, atoi(e));
   if (const char* e = getenv("B200_RANGES")) t->ranges = atoi(e);
   if (const char* e = getenv("B200_ARENA_ENTRIES")) t->arena_entries = atoll(e);
+  if (const char* e = getenv("B200_ROW_CHARGE")) t->row_charge = std::max(0LL, atoll(e));
   t->deterministic = flag("B200_DETERMINISTIC");
   if (t->deterministic) t->on_chip = true;
 }
@@ -1925,28 +1926,47 @@ int check_sorted_device(DevCSR* d, bool validate) {
 }
 
 // ------------------------------------------------------------------------------------------
+// cost of a row for the partition of a step among GPUs: its products, plus a fixed charge for
+// every row heavy enough for the CTA-per-row kernels (their per-row set-up does not shrink with
+// the row: measured on R-MAT scale 20, equal products alone leave the rank that holds the long
+// tail 1.7x slower than the one that holds the hubs).  The reference's static variant balances a
+// footprint of the same kind, (products + nnz(C_i) + 32 + nnz(A_i)) >> 1
+// (nlibs/static_omp_csr_kernel.cc:28-62).
+__global__ void __launch_bounds__(256)
+k_row_cost(long long* __restrict__ flops, int m, long long row_charge, long long heavy_from) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { const long long f = flops[i]; flops[i] = f + (f > heavy_from ? row_charge : 0); }
+}
+
 int flops_prefix_device(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi,
-                        int64_t* d_prefix) {
+                        int64_t* d_prefix, long long row_charge, long long* d_products) {
   Ctx& c = ctx();
   const int m = row_hi - row_lo;
+  Temps T;
   long long* d_flops = nullptr;
   unsigned char* d_bin = nullptr;
   int* d_cnt = nullptr;
-  B200_CUDA(dalloc(&d_flops, (size_t)m + 1));
-  B200_CUDA(dalloc(&d_bin, (size_t)m));
-  B200_CUDA(dalloc(&d_cnt, (size_t)m));
+  B200_CUDA(T.alloc(&d_flops, (size_t)m + 1));
+  B200_CUDA(T.alloc(&d_bin, (size_t)m));
+  B200_CUDA(T.alloc(&d_cnt, (size_t)m));
   B200_CUDA(cudaMemsetAsync(d_flops + m, 0, sizeof(long long), c.stream));
   if (m > 0)
     k_row_flops<<<(unsigned)(((long long)m * 8 + 255) / 256), 256, 0, c.stream>>>(
         A.rowptr, A.col, B.rowptr, row_lo, m, 8192LL, d_flops, d_bin, d_cnt);
   void* tmp = nullptr;
   size_t tb = 0;
+  if (d_products) {   // the plain product count, before any charge
+    cub::DeviceReduce::Sum(nullptr, tb, d_flops, d_products, m, c.stream);
+    B200_CUDA(T.alloc((char**)&tmp, tb ? tb : 1));
+    cub::DeviceReduce::Sum(tmp, tb, d_flops, d_products, m, c.stream);
+  }
+  if (row_charge > 0 && m > 0) k_row_cost<<<(m + 255) / 256, 256, 0, c.stream>>>(d_flops, m, row_charge, 512);
+  tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flops, (long long*)d_prefix, m + 1, c.stream);
-  B200_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, c.stream));
-  cub::DeviceScan::ExclusiveSum(tmp, tb, d_flops, (long long*)d_prefix, m + 1, c.stream);
+  void* tmp2 = nullptr;
+  B200_CUDA(T.alloc((char**)&tmp2, tb ? tb : 1));
+  cub::DeviceScan::ExclusiveSum(tmp2, tb, d_flops, (long long*)d_prefix, m + 1, c.stream);
   B200_CUDA(cudaGetLastError());
-  cudaFreeAsync(tmp, c.stream);
-  dfree(d_flops); dfree(d_bin); dfree(d_cnt);
   return B200_OK;
 }
 
