@@ -588,9 +588,8 @@ def run_b200(args):
     # arrayEqualPartition64 on the flops prefix) leaves the rank that holds the long tail of
     # lighter rows 1.7x slower than the rank that holds the hubs (measured at N=4: 50 / 63 / 75 /
     # 84 ms per rank); a charge of 32K products per heavy row gives 69 / 68 / 67 / 67 ms.
-    per_row = np.diff(prefix)
-    cost = per_row + args.row_charge * (per_row > 512)
-    cost_prefix = np.concatenate([[0], np.cumsum(cost)]).astype(np.int64)
+    # (b200_cost_prefix: the library's own cost model, the same the sharded rMCL loop cuts with)
+    cost_prefix = smf.cost_prefix(dA, dA, args.row_charge)
     ends = smf.arrayEqualPartition64(cost_prefix, world)
     lo, hi = int(ends[rank]), int(ends[rank + 1])
 

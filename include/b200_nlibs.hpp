@@ -187,6 +187,39 @@ struct CSR {
     return true;
   }
 
+  // plain-text form used by the driver's --output / --expect: "rows cols nnz", then one
+  // "row col value" line per entry (0-based, %.17g: values survive the round trip bit for bit)
+  void writeText(const char* fname) const {
+    FILE* f = fopen(fname, "w");
+    if (!f) { printf("Failed to open file %s\n", fname); exit(-1); }
+    fprintf(f, "%d %d %d\n", rows, cols, nnz);
+    for (int i = 0; i < rows; ++i)
+      for (int p = rowPtr[i]; p < rowPtr[i + 1]; ++p) fprintf(f, "%d %d %.17g\n", i, colInd[p], values[p]);
+    fclose(f);
+  }
+  static CSR readText(const char* fname) {
+    FILE* f = fopen(fname, "r");
+    if (!f) { printf("Failed to open file %s\n", fname); exit(-1); }
+    CSR m;
+    if (fscanf(f, "%d %d %d", &m.rows, &m.cols, &m.nnz) != 3) { printf("bad header in %s\n", fname); exit(-1); }
+    m.rowPtr = (int*)calloc((size_t)m.rows + 1, sizeof(int));
+    m.colInd = (int*)malloc(((size_t)m.nnz + 1) * sizeof(int));
+    m.values = (QValue*)malloc(((size_t)m.nnz + 1) * sizeof(QValue));
+    int last = 0;
+    for (int p = 0; p < m.nnz; ++p) {
+      int r;
+      if (fscanf(f, "%d %d %lf", &r, &m.colInd[p], &m.values[p]) != 3 || r < last || r >= m.rows) {
+        printf("bad entry %d in %s (entries must come row by row)\n", p, fname);
+        exit(-1);
+      }
+      m.rowPtr[r + 1]++;
+      last = r;
+    }
+    for (int i = 0; i < m.rows; ++i) m.rowPtr[i + 1] += m.rowPtr[i];
+    fclose(f);
+    return m;
+  }
+
   // products of A x B, counted exactly (the reference's getSpMMFlops in this fork only counts
   // rows with > 1024 products, nlibs/cpu_csr_kernel.cc:58-72)
   long long spMMFlops(const CSR& B) const {
@@ -227,6 +260,38 @@ inline void omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const
                          const int IB[], const int JB[], const QValue B[], const int nnzB,
                          int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
                          const int n, const int stride) {
+  flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
+}
+// The other SpMM variants of nlibs/cpu_csr_kernel.h:73-98 (thread-scratch overloads included):
+// the reference's variants differ in how they partition rows among threads — static_omp by a
+// per-row FOOTPRINT (nlibs/static_omp_csr_kernel.cc:28-95), flops_omp by products, omp by dynamic
+// chunks — and produce bit-identical results; here one device pipeline serves
+// them all, and the footprint-style cost model is what b200_cost_prefix exposes for cutting a
+// product among GPUs.
+inline void omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                         const int IB[], const int JB[], const QValue B[], const int nnzB,
+                         int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                         const int n, const thread_data_t* thread_datas, const int stride) {
+  (void)thread_datas;
+  flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
+}
+inline void static_omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                                const int IB[], const int JB[], const QValue B[], const int nnzB,
+                                int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                                const int n, const int stride) {
+  flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
+}
+inline void static_omp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                                const int IB[], const int JB[], const QValue B[], const int nnzB,
+                                int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                                const int n, const thread_data_t* thread_datas, const int stride) {
+  (void)thread_datas;
+  flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
+}
+inline void noindex_somp_CSR_SpMM(const int IA[], const int JA[], const QValue A[], const int nnzA,
+                                  const int IB[], const int JB[], const QValue B[], const int nnzB,
+                                  int*& IC, int*& JC, QValue*& C, int& nnzC, const int m, const int k,
+                                  const int n, const int stride) {
   flops_omp_CSR_SpMM(IA, JA, A, nnzA, IB, JB, B, nnzB, IC, JC, C, nnzC, m, k, n, stride);
 }
 inline void static_omp_CSR_RMCL_OneStep(const int IA[], const int JA[], const QValue A[], const int nnzA,
@@ -468,7 +533,13 @@ struct Options {
   RunOptions rmclOption;  // --rmclOptions / -r {SEQ,OMP,GPU,CILK,SOMP,MKL,SFOMP,HYB,B200}: all run the B200 path
   bool stats, calcChange;
   double eps;          // --eps: stationary-chaos stopping rule (not in the reference; 0 = fixed count)
-  Options() : maxIters(5), stride(512), rmclOption(B200), stats(false), calcChange(false), eps(0.0) { inputFileName[0] = 0; }
+  // --expect FILE: the final Mt to compare with ("rows cols nnz", then "row col value" lines,
+  // 0-based): the driver then ends with nrmcl.cc's verdict line, Same or Diffs (nrmcl.cc:27-32);
+  // --output FILE: write the final Mt in that format
+  char expectFileName[1024], outputFileName[1024];
+  Options() : maxIters(5), stride(512), rmclOption(B200), stats(false), calcChange(false), eps(0.0) {
+    inputFileName[0] = 0; expectFileName[0] = 0; outputFileName[0] = 0;
+  }
 };
 inline int process_args(int argc, char** argv, Options& options) {
   static const char* names[] = {"SEQ", "OMP", "GPU", "CILK", "SOMP", "MKL", "SFOMP", "HYB", "B200"};
@@ -480,6 +551,8 @@ inline int process_args(int argc, char** argv, Options& options) {
     else if (is("--maxIters", "-m") && v) { options.maxIters = atoi(v); ++a; }
     else if (is("--stride", NULL) && v) { options.stride = atoi(v); ++a; }
     else if (is("--eps", NULL) && v) { options.eps = atof(v); ++a; }
+    else if (is("--expect", NULL) && v) { strncpy(options.expectFileName, v, sizeof(options.expectFileName) - 1); ++a; }
+    else if (is("--output", NULL) && v) { strncpy(options.outputFileName, v, sizeof(options.outputFileName) - 1); ++a; }
     else if (is("--rmclOptions", "-r") && v) {
       for (int r = 0; r < 9; ++r) if (!strcmp(v, names[r])) options.rmclOption = (RunOptions)r;
       ++a;
@@ -550,6 +623,40 @@ struct PCSR {
     for (int b = 0; b < c; ++b) parts[b].dispose();
     return out;
   }
+};
+
+// The same container for DEVICE matrices: dB = B.toGpuCSR(); the stripes are cut on the device
+// (b200_csr_column_stripe), every stripe multiplied there (gpuSpMMWrapper) and the results glued
+// back row by row (b200_csr_concat_cols) — nothing travels to the host.
+struct DevicePCSR {
+  int rows, cols, c;
+  std::vector<CSR> blocks;   // device-resident stripes
+  int stride() const { return (cols + c - 1) / c; }
+  DevicePCSR(const CSR& dB, const int c) : rows(dB.rows), cols(dB.cols), c(c) {
+    for (int b = 0; b < c && b * stride() < cols; ++b) {
+      CSR blk;
+      blk.rows = rows; blk.cols = std::min(cols, (b + 1) * stride()) - b * stride();
+      b200_check(b200_csr_column_stripe(dB.device, b * stride(), std::min(cols, (b + 1) * stride()), &blk.device),
+                 "b200_csr_column_stripe");
+      long long z = 0;
+      b200_check(b200_csr_info(blk.device, &blk.rows, &blk.cols, &z), "b200_csr_info");
+      blk.nnz = (int)z;
+      blocks.push_back(blk);
+    }
+  }
+  CSR leftMultiply(const CSR& dA) const {
+    std::vector<CSR> parts;
+    std::vector<b200_csr_t> hs;
+    for (size_t b = 0; b < blocks.size(); ++b) { parts.push_back(gpuSpMMWrapper(dA, blocks[b])); hs.push_back(parts.back().device); }
+    CSR out;
+    b200_check(b200_csr_concat_cols(hs.data(), (int)hs.size(), &out.device), "b200_csr_concat_cols");
+    long long z = 0;
+    b200_check(b200_csr_info(out.device, &out.rows, &out.cols, &z), "b200_csr_info");
+    out.nnz = (int)z;
+    for (size_t b = 0; b < parts.size(); ++b) parts[b].deviceDispose();
+    return out;
+  }
+  void dispose() { for (size_t b = 0; b < blocks.size(); ++b) blocks[b].deviceDispose(); blocks.clear(); }
 };
 
 }  // namespace nlibs

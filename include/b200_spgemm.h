@@ -78,6 +78,12 @@ int b200_finalize(void);
 /* Developer switches (B200_* environment variables) are read once by b200_init;
  * this re-reads them (tests and A/B measurements change them between calls). */
 int b200_options_reload(void);
+/* Opt-in top-k pruning of the rMCL steps (every entry point below that runs one): of the entries
+ * of a row that pass the reference's threshold (nlibs/tools/util.cc:4-9, 47-69) only the k
+ * largest stay — equal values ranked by ascending column — and the row is normalised over them.
+ * 0 (the default) switches it off: the reference has the threshold rule only,
+ * and parity runs use that.  oracle/oracle.c states the same rule for the checker. */
+int b200_set_topk(int k);
 const char* b200_last_error(void);
 /* The CUDA stream (a cudaStream_t) every kernel of this library is launched on, so that a
  * harness can bracket calls with its own CUDA events. */
@@ -193,6 +199,13 @@ int b200_rmcl_step_device_rows(b200_csr_t Mgt, b200_csr_t Mt, int row_lo, int ro
  * Replaces dynamic_omp_CSR_flops (nlibs/flops_csr_kernel.cc:14-31).  `prefix` is a host
  * array of rows+1 long long. */
 int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix);
+/* The same prefix over a per-row COST: products plus `row_charge` for every row heavy enough for
+ * the CTA-per-row kernels (more than 512 products) — the device analogue of the footprint
+ * static_omp_CSR_SpMM balances, (products + nnz(C_i) + 32 + nnz(A_i)) >> 1
+ * (nlibs/static_omp_csr_kernel.cc:28-62, dynamic_omp_CSR_IC_nnzC_footprints :68-95): with
+ * b200_equal_partition64 it cuts a product into row blocks of equal TIME for several GPUs.
+ * row_charge < 0: the library's default (32768, measured on R-MAT scale 20; B200_ROW_CHARGE). */
+int b200_cost_prefix(b200_csr_t A, b200_csr_t B, long long row_charge, long long* prefix);
 /* Equal-flops contiguous row cut points, ends[0..nparts].  Same arithmetic as
  * arrayEqualPartition64 (nlibs/tools/util.cc:123-135); host-only, no device needed. */
 int b200_equal_partition64(const long long* prefix, int n, int nparts, int* ends);
@@ -202,6 +215,15 @@ int b200_equal_partition64(const long long* prefix, int n, int nparts, int* ends
 int b200_csr_row_argmax(b200_csr_t h, int* labels);
 /* Concatenate row blocks (device) into one CSR: the all-gather's local assembly step. */
 int b200_csr_concat_rows(const b200_csr_t* blocks, int nblocks, b200_csr_t* out);
+
+/* Column stripe B[:, col_lo:col_hi) as a device CSR with LOCAL column indices (column - col_lo):
+ * one block of the reference's PCSR (nlibs/PCSR.h:5-101, PCSR.cc:3-56; stripe b of c is
+ * [b * stride, min(cols, (b + 1) * stride)) with stride = ceil(cols / c)).  A x stripe through
+ * b200_spgemm_device is the column-striped product of PCSR::leftMultiply
+ * (correctTests/pcsrTest.cc:7-19); b200_csr_concat_cols glues the per-stripe results back
+ * together row by row (block b's columns shifted by the widths of the blocks before it). */
+int b200_csr_column_stripe(b200_csr_t B, int col_lo, int col_hi, b200_csr_t* out);
+int b200_csr_concat_cols(const b200_csr_t* blocks, int nblocks, b200_csr_t* out);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) --------------------------------
  * Not in the reference (single GPU, SURVEY.md §2.1 strategy table).  The 128-byte unique id

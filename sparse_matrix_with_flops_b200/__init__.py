@@ -6,13 +6,13 @@ interface on top of it.  Importing the package does not need a GPU; the first ca
 computes does, and fails loudly without one (there is no CPU fallback).
 """
 from . import _lib
-from .csr import (COO_DEDUP, COO_NORMALISE, COO_SELF_LOOPS, CSR, DeviceCSR, RMCL,
+from .csr import (COO_DEDUP, COO_NORMALISE, COO_SELF_LOOPS, CSR, DeviceCSR, DevicePCSR, RMCL,
                   arrayEqualPartition64, comm_destroy, comm_init, cooToGpuCSR, rmclInitDevice,
-                  comm_unique_id, flops_prefix, gpuRmclIter, gpuRmclIterSharded, gpuRmclOneStep,
-                  gpuSpMMWrapper, init, reload_options, rmclInit, synth_planted, synth_rmat, synth_stencil27)
+                  comm_unique_id, cost_prefix, flops_prefix, gpuRmclIter, gpuRmclIterSharded, gpuRmclOneStep,
+                  gpuSpMMWrapper, init, reload_options, rmclInit, set_topk, synth_planted, synth_rmat, synth_stencil27)
 
 __all__ = ["COO_DEDUP", "COO_NORMALISE", "COO_SELF_LOOPS", "cooToGpuCSR", "rmclInitDevice",
-           "CSR", "DeviceCSR", "RMCL", "arrayEqualPartition64", "comm_destroy", "comm_init",
-           "comm_unique_id", "flops_prefix", "gpuRmclIter", "gpuRmclIterSharded",
-           "gpuRmclOneStep", "gpuSpMMWrapper", "init", "reload_options", "rmclInit", "synth_planted", "synth_rmat",
+           "CSR", "DeviceCSR", "DevicePCSR", "RMCL", "arrayEqualPartition64", "comm_destroy", "comm_init",
+           "comm_unique_id", "cost_prefix", "flops_prefix", "gpuRmclIter", "gpuRmclIterSharded",
+           "gpuRmclOneStep", "gpuSpMMWrapper", "init", "reload_options", "set_topk", "rmclInit", "synth_planted", "synth_rmat",
            "synth_stencil27", "_lib"]

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200_init": (C.c_int, [C.c_int]),
     "b200_finalize": (C.c_int, []),
     "b200_options_reload": (C.c_int, []),
+    "b200_set_topk": (C.c_int, [C.c_int]),
     "b200_last_error": (C.c_char_p, []),
     "b200_stream": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b200_device_info": (C.c_int, [c_int_p, c_ll_p, C.c_char_p, C.c_int]),
@@ -96,9 +97,12 @@ SIGNATURES = {
     "b200_rmcl_step_device_rows": (C.c_int, [csr_t, csr_t, C.c_int, C.c_int, C.POINTER(csr_t),
                                              c_double_p, C.POINTER(Stats)]),
     "b200_flops_prefix": (C.c_int, [csr_t, csr_t, c_ll_p]),
+    "b200_cost_prefix": (C.c_int, [csr_t, csr_t, C.c_longlong, c_ll_p]),
     "b200_equal_partition64": (C.c_int, [c_ll_p, C.c_int, C.c_int, c_int_p]),
     "b200_csr_row_argmax": (C.c_int, [csr_t, c_int_p]),
     "b200_csr_concat_rows": (C.c_int, [C.POINTER(csr_t), C.c_int, C.POINTER(csr_t)]),
+    "b200_csr_column_stripe": (C.c_int, [csr_t, C.c_int, C.c_int, C.POINTER(csr_t)]),
+    "b200_csr_concat_cols": (C.c_int, [C.POINTER(csr_t), C.c_int, C.POINTER(csr_t)]),
     "b200_comm_unique_id": (C.c_int, [C.c_char_p]),
     "b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "b200_comm_destroy": (C.c_int, []),

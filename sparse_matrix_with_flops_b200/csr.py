@@ -38,6 +38,12 @@ def reload_options():
     check(_lib.load().b200_options_reload())
 
 
+def set_topk(k):
+    """b200_set_topk: keep at most k entries per row in every rMCL step (0 = off, the default)."""
+    _ensure_init()
+    check(_lib.load().b200_set_topk(int(k)))
+
+
 def _ensure_init():
     if _inited["device"] is None:
         init(0)
@@ -199,6 +205,13 @@ class DeviceCSR:
         return CSR(_take(V, nnz.value, np.float64), _take(J, nnz.value, np.int32),
                    _take(I, m + 1, np.int32), m, cols, nnz.value)
 
+    def column_stripe(self, col_lo, col_hi):
+        """b200_csr_column_stripe: B[:, col_lo:col_hi) with local columns — one PCSR block
+        (nlibs/PCSR.cc:3-56) on the device."""
+        h = csr_t()
+        check(_lib.load().b200_csr_column_stripe(self.handle, int(col_lo), int(col_hi), C.byref(h)))
+        return DeviceCSR(h)
+
     def makeOrdered(self):
         """CSR::makeOrdered (nlibs/CSR.cc:73-86) on the device."""
         check(_lib.load().b200_csr_sort_rows(self.handle))
@@ -228,6 +241,33 @@ def gpuSpMMWrapper(dA, dB, row_lo=None, row_hi=None, want_stats=False):
         check(lib.b200_spgemm_device_rows(dA.handle, dB.handle, row_lo, row_hi, C.byref(h), C.byref(st)))
     out = DeviceCSR(h)
     return (out, st.as_dict()) if want_stats else out
+
+
+class DevicePCSR:
+    """The reference's PCSR (nlibs/PCSR.h:5-101) on the device: c column stripes of width
+    ceil(cols / c), block b with local columns; leftMultiply = A x every stripe, glued back row
+    by row (PCSR::leftMultiply, correctTests/pcsrTest.cc:7-19)."""
+
+    def __init__(self, dB, c):
+        rows, cols, _ = dB.info()
+        self.rows, self.cols, self.c = rows, cols, int(c)
+        self.stride = (cols + self.c - 1) // self.c
+        self.blocks = [dB.column_stripe(b * self.stride, min(cols, (b + 1) * self.stride))
+                       for b in range(self.c) if b * self.stride < cols]
+
+    def leftMultiply(self, dA):
+        parts = [gpuSpMMWrapper(dA, blk) for blk in self.blocks]
+        arr = (csr_t * len(parts))(*[p.handle for p in parts])
+        h = csr_t()
+        check(_lib.load().b200_csr_concat_cols(arr, len(parts), C.byref(h)))
+        for p in parts:
+            p.deviceDispose()
+        return DeviceCSR(h)
+
+    def dispose(self):
+        for blk in self.blocks:
+            blk.deviceDispose()
+        self.blocks = []
 
 
 def gpuRmclOneStep(dMgt, dMt, row_lo=None, row_hi=None, want_stats=False):
@@ -363,6 +403,16 @@ def flops_prefix(dA, dB):
     lib = _lib.load()
     out = np.empty(dA.rows + 1, dtype=np.int64)
     check(lib.b200_flops_prefix(dA.handle, dB.handle, out.ctypes.data_as(_lib.c_ll_p)))
+    return out
+
+
+def cost_prefix(dA, dB, row_charge=-1):
+    """b200_cost_prefix: prefix of products + row_charge per heavy row (the device analogue of
+    static_omp's footprint, nlibs/static_omp_csr_kernel.cc:28-95); -1 = the library's default."""
+    lib = _lib.load()
+    rows = dA.info()[0]
+    out = np.zeros(rows + 1, dtype=np.int64)
+    check(lib.b200_cost_prefix(dA.handle, dB.handle, int(row_charge), out.ctypes.data_as(_lib.c_ll_p)))
     return out
 
 

@@ -493,6 +493,12 @@ int b200_init(int device) {
   return B200_OK;
 }
 
+int b200_set_topk(int k) {
+  if (k < 0) { set_error("top-k must be >= 0 (0 = off)"); return B200_ERR_BAD_ARG; }
+  ctx().topk = k;
+  return B200_OK;
+}
+
 int b200_options_reload(void) {
   load_tunables(&ctx().tun);
   return B200_OK;
@@ -774,6 +780,10 @@ int b200_rmcl_step_device(b200_csr_t Mgt, b200_csr_t Mt, b200_csr_t* newMt, doub
 }
 
 int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix) {
+  return b200_cost_prefix(A, B, 0, prefix);
+}
+
+int b200_cost_prefix(b200_csr_t A, b200_csr_t B, long long row_charge, long long* prefix) {
   B200_REQUIRE_INIT();
   int rc = check_mul(A, B, 0, A ? A->d.rows : 0);
   if (rc) return rc;
@@ -783,7 +793,7 @@ int b200_flops_prefix(b200_csr_t A, b200_csr_t B, long long* prefix) {
   Temps T;
   int64_t* d_prefix = nullptr;
   B200_CUDA(T.alloc(&d_prefix, (size_t)m + 1));
-  rc = flops_prefix_device(A->d, B->d, 0, m, d_prefix);
+  rc = flops_prefix_device(A->d, B->d, 0, m, d_prefix, row_charge < 0 ? c.tun.row_charge : row_charge);
   if (rc) return rc;
   B200_CUDA(cudaMemcpyAsync(prefix, d_prefix, ((size_t)m + 1) * sizeof(long long),
                             cudaMemcpyDeviceToHost, c.stream));
@@ -841,6 +851,37 @@ int b200_csr_concat_rows(const b200_csr_t* blocks, int nblocks, b200_csr_t* out)
   B200_CUDA(cudaStreamSynchronize(ctx().stream));
   b200_csr* h = new b200_csr();
   h->d = d;
+  *out = h;
+  return B200_OK;
+}
+
+int b200_csr_column_stripe(b200_csr_t B, int col_lo, int col_hi, b200_csr_t* out) {
+  B200_REQUIRE_INIT();
+  if (!B || !out || col_lo < 0 || col_hi < col_lo || col_hi > B->d.cols) {
+    set_error("bad column stripe");
+    return B200_ERR_BAD_ARG;
+  }
+  b200_csr* h = new b200_csr();
+  const int rc = column_stripe_device(B->d, col_lo, col_hi, &h->d);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return B200_OK;
+}
+
+int b200_csr_concat_cols(const b200_csr_t* blocks, int nblocks, b200_csr_t* out) {
+  B200_REQUIRE_INIT();
+  if (!blocks || nblocks < 1 || !out) { set_error("bad argument"); return B200_ERR_BAD_ARG; }
+  std::vector<DevCSR> v;
+  long long cols = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    if (!blocks[b] || blocks[b]->d.rows != blocks[0]->d.rows) { set_error("stripes disagree on rows"); return B200_ERR_BAD_ARG; }
+    cols += blocks[b]->d.cols;
+    v.push_back(blocks[b]->d);
+  }
+  if (cols > INT_MAX) { set_error("too many columns"); return B200_ERR_INT32_OVERFLOW; }
+  b200_csr* h = new b200_csr();
+  const int rc = concat_cols_device(v, &h->d);
+  if (rc) { delete h; return rc; }
   *out = h;
   return B200_OK;
 }

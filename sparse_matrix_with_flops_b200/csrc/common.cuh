@@ -85,6 +85,7 @@ struct Ctx {
   int* arena_col = nullptr;
   double* arena_val = nullptr;
   size_t arena_cap = 0;
+  int topk = 0;                // rMCL: keep at most this many entries per row (b200_set_topk; 0 = off)
   long long arena_budget = 0;  // entries a row tile of an rMCL step may hold (tiles.cu); 0: not sized yet
   // small read-backs (row totals, bin counts): a kernel writes them into mapped pinned memory
   // instead of a cudaMemcpy, because the device-to-host copy engine may be busy for 100+ ms with
@@ -182,6 +183,10 @@ int sorted_copy_of(const DevCSR& d, DevCSR* out);
 // concatenation of row blocks (tiles.cu); arrayEqualPartition64 on a device prefix (tiles.cu)
 int concat_rows_device(const std::vector<DevCSR>& blocks, int cols, DevCSR* out);
 int equal_partition_device(const int64_t* d_prefix, int n, int nparts, int* h_ends);
+// column stripe B[:, lo:hi) with local column indices, and the row-wise re-assembly of stripes
+// (stripes.cu: the device PCSR, nlibs/PCSR.cc:3-56)
+int column_stripe_device(const DevCSR& B, int lo, int hi, DevCSR* out);
+int concat_cols_device(const std::vector<DevCSR>& blocks, DevCSR* out);
 
 // CSR::makeOrdered on the device (spgemm.cu)
 int sort_rows_device(DevCSR* d);

@@ -386,7 +386,35 @@ struct RmclOut {          // where a fused rMCL row goes
   long long* row_off;           // [m] arena offset of the row
   int* row_kept;                // [m] kept entries
   unsigned long long* chaos_bits;  // max over rows of (max - sum sq), as ordered bits
+  int topk;                        // > 0: keep at most this many entries per row (b200_set_topk)
 };
+
+// ---- top-k pruning (opt-in; not in the reference, whose rule is the threshold alone, SURVEY.md
+// §8a; oracle/oracle.c states the same rule for the checker).  Of the entries that pass the
+// threshold the k largest stay; equal values are ranked by ascending column.  The cut is found
+// without sorting: the k-th largest value by bisection on the bit pattern of the (non-negative)
+// values, then the last admitted column among its ties by bisection on the column.
+// count(pred) sums over the row: warp-wide or block-wide, supplied by the caller.
+template <typename Count>
+__device__ __forceinline__ void topk_cut(Count count, double thresh, double rmax, int k, int ncols,
+                                         double* tk_out, int* cstar_out) {
+  unsigned long long lo = (unsigned long long)__double_as_longlong(thresh);
+  unsigned long long hi = (unsigned long long)__double_as_longlong(rmax) + 1ull;
+  while (hi - lo > 1ull) {   // count(v >= lo) >= k > count(v >= hi)
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    const double m = __longlong_as_double((long long)mid);
+    if (count([&](double v, int) { return v >= m; }) >= k) lo = mid; else hi = mid;
+  }
+  const double tk = __longlong_as_double((long long)lo);
+  const int need = k - count([&](double v, int) { return v > tk; });  // ties to admit, >= 1
+  int clo = -1, chi = ncols - 1;   // count(v == tk, col <= clo) < need <= count(v == tk, col <= chi)
+  while (chi - clo > 1) {
+    const int mid = clo + ((chi - clo) >> 1);
+    if (count([&](double v, int c) { return v == tk && c <= mid; }) >= need) chi = mid; else clo = mid;
+  }
+  *tk_out = tk;
+  *cstar_out = chi;
+}
 
 // numeric, one warp per row, CAP output entries per warp (indexProcessCRowI,
 // cpu_csr_kernel.h:134-188) + sort (+ fused rMCL epilogue when RMCL).
@@ -491,12 +519,28 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
     rsum = __dadd_rn(rsum, v);
   }
   const double thresh = compute_threshold(__ddiv_rn(rsum, (double)cnt), rmax);
+  // opt-in top-k: the cut (tk, cstar) narrows the keep rule to the k largest entries
+  double tk = 0.0;
+  int cstar = 0x7fffffff;
+  bool cut = false;
+  if (ro.topk > 0) {
+    auto wcount = [&](auto pred) {
+      int c = 0;
+      for (int k = lane; k < cnt; k += 32) c += (vals[k] >= thresh && pred(vals[k], cols[k])) ? 1 : 0;
+      return warp_sum_int(c);
+    };
+    if (wcount([](double, int) { return true; }) > ro.topk) {
+      cut = true;
+      topk_cut(wcount, thresh, rmax, ro.topk, 0x7fffffff, &tk, &cstar);
+    }
+  }
+  auto keeps = [&](double v, int c) { return v >= thresh && (!cut || v > tk || (v == tk && c <= cstar)); };
   double ksum = 0.0;
   int kept = 0;
 #pragma unroll 4
   for (int k = 0; k < cnt; ++k) {
     const double v = vals[k];
-    const bool keep = v >= thresh;
+    const bool keep = keeps(v, cols[k]);
     ksum = keep ? __dadd_rn(ksum, v) : ksum;
     kept += keep ? 1 : 0;
   }
@@ -508,7 +552,7 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
   for (int k0 = 0; k0 < cnt; k0 += 32) {
     const int k = k0 + lane;
     const double v = (k < cnt) ? vals[k] : 0.0;
-    const bool keep = (k < cnt) && (v >= thresh);
+    const bool keep = (k < cnt) && keeps(v, cols[k]);
     const unsigned km = __ballot_sync(FULL, keep);
     if (keep) {
       const double w = __ddiv_rn(v, ksum);
@@ -1174,11 +1218,27 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     const double rsum = block_sum_d<BT>(psum, s_redd);
     const double rmax = block_max_d<BT>(pmax, s_redd);
     const double thresh = compute_threshold(__ddiv_rn(rsum, (double)cnt), rmax);
+    // opt-in top-k (see topk_cut): block-wide counts
+    double tk = 0.0;
+    int cstar = 0x7fffffff;
+    bool cut = false;
+    if (ro.topk > 0) {
+      auto bcount = [&](auto pred) {
+        int c = 0;
+        for (int k = threadIdx.x; k < cnt; k += BT) c += (acc[k] >= thresh && pred(acc[k], ocol[k])) ? 1 : 0;
+        return block_sum_int<BT>(c, s_red);
+      };
+      if (bcount([](double, int) { return true; }) > ro.topk) {
+        cut = true;
+        topk_cut(bcount, thresh, rmax, ro.topk, 0x7fffffff, &tk, &cstar);
+      }
+    }
+    auto keeps = [&](double v, int c) { return v >= thresh && (!cut || v > tk || (v == tk && c <= cstar)); };
     double ksum_p = 0.0;
     int kept_p = 0;
     for (int k = threadIdx.x; k < cnt; k += BT) {
       const double v2 = acc[k];
-      if (v2 >= thresh) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
+      if (keeps(v2, ocol[k])) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
     }
     const double ksum = block_sum_d<BT>(ksum_p, s_redd);
     const int kept = block_sum_int<BT>(kept_p, s_red);
@@ -1187,7 +1247,7 @@ k_num_bitmap(const int* __restrict__ list, int count, int row_lo,
     int written = 0;
     for (int k0 = 0; k0 < cnt; k0 += BT) {
       const int k = k0 + threadIdx.x;
-      const bool keep = (k < cnt) && (acc[k] >= thresh);
+      const bool keep = (k < cnt) && keeps(acc[k], ocol[k]);
       int tot;
       const int ex = block_excl_scan<BT>(keep ? 1 : 0, s_red, &tot);
       if (keep) {
@@ -1679,11 +1739,27 @@ k_rmcl_epilogue_rows(const int* __restrict__ list, int count, const int64_t* __r
     const double rsum = block_sum_d<BT>(psum, s_redd);
     const double rmax = block_max_d<BT>(pmax, s_redd);
     const double thresh = compute_threshold(__ddiv_rn(rsum, (double)cnt), rmax);
+    // opt-in top-k (see topk_cut): block-wide counts
+    double tk = 0.0;
+    int cstar = 0x7fffffff;
+    bool cut = false;
+    if (ro.topk > 0) {
+      auto bcount = [&](auto pred) {
+        int c = 0;
+        for (int k = threadIdx.x; k < cnt; k += BT) c += (acc[k] >= thresh && pred(acc[k], col[k])) ? 1 : 0;
+        return block_sum_int<BT>(c, s_red);
+      };
+      if (bcount([](double, int) { return true; }) > ro.topk) {
+        cut = true;
+        topk_cut(bcount, thresh, rmax, ro.topk, 0x7fffffff, &tk, &cstar);
+      }
+    }
+    auto keeps = [&](double v, int c) { return v >= thresh && (!cut || v > tk || (v == tk && c <= cstar)); };
     double ksum_p = 0.0;
     int kept_p = 0;
     for (int k = threadIdx.x; k < cnt; k += BT) {
       const double v2 = acc[k];
-      if (v2 >= thresh) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
+      if (keeps(v2, col[k])) { ksum_p = __dadd_rn(ksum_p, v2); ++kept_p; }
     }
     const double ksum = block_sum_d<BT>(ksum_p, s_redd);
     const int kept = block_sum_int<BT>(kept_p, s_red);
@@ -1693,7 +1769,7 @@ k_rmcl_epilogue_rows(const int* __restrict__ list, int count, const int64_t* __r
       const int k = k0 + threadIdx.x;
       const double v2 = (k < cnt) ? acc[k] : 0.0;
       const int c = (k < cnt) ? col[k] : 0;
-      const bool keep = (k < cnt) && (v2 >= thresh);
+      const bool keep = (k < cnt) && keeps(v2, c);
       int tot;
       // (the scan's barriers separate this chunk's reads from the writes below, which land at
       // or before the positions just read: compaction only moves entries to the left)
@@ -2388,6 +2464,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ro.chaos_bits = d_cursor + 1;
     ro.row_off = d_rowoff;
     ro.row_kept = d_kept;
+    ro.topk = c.topk;
     if (nbig_num && !use_parts) {
       scr_stride = n;  // a row has at most n distinct columns
       B200_CUDA(T.alloc(&d_scr_col, (size_t)std::min(nbig_num, c.sm_count) * scr_stride));

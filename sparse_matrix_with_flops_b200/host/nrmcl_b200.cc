@@ -3,6 +3,8 @@
 // only: every computation goes through include/b200_nlibs.hpp -> libb200spgemm.so.
 //
 //   nrmcl_b200.x --input FILE [--maxIters N] [--rmclOptions B200] [--eps E]     (nrmcl.cc's flags)
+//                [--expect FILE]   ends with nrmcl.cc's verdict line: Same / Diffs (exit code 0 / 1)
+//                [--output FILE]   writes the final Mt ("rows cols nnz", then "row col value" lines)
 //   nrmcl_b200.x rmcl  <rmat|stencil|planted> <size> [maxIters] [eps]
 //   nrmcl_b200.x spmm  <rmat|stencil|planted> <size> [reps]
 //   nrmcl_b200.x spmm-host <rmat|stencil|planted> <size> [reps]   (host CSR in, host row blocks out)
@@ -53,9 +55,23 @@ static int run_file(int argc, char* argv[]) {
     attractors.insert(best);
   }
   printf("iters %d final nnz %d clusters %zu\n", iters, Mt.nnz, attractors.size());
+  if (options.outputFileName[0]) Mt.writeText(options.outputFileName);
+  int ret = 0;
+  if (options.expectFileName[0]) {
+    // nrmcl.cc:25-32: both matrices ordered, compared, one verdict line.  The matrix to compare
+    // with comes from a file here (the reference computes it with its SEQ path in the same
+    // process; this library has no second path to compute it with)
+    CSR want = CSR::readText(options.expectFileName);
+    want.makeOrdered();
+    Mt.makeOrdered();
+    const bool isSame = Mt.isEqual(want);
+    printf(isSame ? "Same\n" : "Diffs\n");
+    ret = isSame ? 0 : 1;
+    want.dispose();
+  }
   Mt.dispose();
   b200_finalize();
-  return 0;
+  return ret;
 }
 
 int main(int argc, char* argv[]) {

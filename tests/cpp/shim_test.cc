@@ -49,6 +49,15 @@ int main() {
   diffs += report("flops_spmm vs dense product", C1.isEqual(W, 1e-12));
   diffs += report("omp_spmm vs flops_spmm", C2.isEqual(C1, 0.0));
   diffs += report("flops_omp_CSR_SpMM vs flops_spmm", C3.isEqual(C1, 0.0));
+  {  // static_omp_CSR_SpMM with thread scratch, the SOMP variant's raw entry point (cpu_csr_kernel.h:91-94)
+    int *I2, *J2, nnz2; QValue* V2;
+    static_omp_CSR_SpMM(A.rowPtr, A.colInd, A.values, A.nnz, A.rowPtr, A.colInd, A.values, A.nnz, I2, J2, V2, nnz2,
+                        n, n, n, (const thread_data_t*)NULL, 512);
+    CSR C6(V2, J2, I2, n, n, nnz2);
+    C6.makeOrdered();
+    diffs += report("static_omp_CSR_SpMM vs flops_spmm", C6.isEqual(C1, 0.0));
+    C6.dispose();
+  }
   // device round trip + gpuSpMMWrapper
   CSR dA = A.toGpuCSR();
   CSR dC = gpuSpMMWrapper(dA, dA);
@@ -82,6 +91,15 @@ int main() {
   diffs += report("PCSR(3) product vs plain", C5.isEqual(C1, 1e-12));
   diffs += report("PCSR nnz", P.nnz() == A.nnz);
   P.dispose();
+  {  // the same container on device matrices: stripes cut, multiplied and glued on the device
+    CSR dA2 = A.toGpuCSR();
+    DevicePCSR DP(dA2, 3);
+    CSR dC7 = DP.leftMultiply(dA2);
+    CSR C7 = dC7.toCpuCSR();
+    C7.makeOrdered();
+    diffs += report("DevicePCSR(3) product vs plain", C7.isEqual(C1, 1e-12));
+    dC7.deviceDispose(); DP.dispose(); dA2.deviceDispose();
+  }
   // rMCL: rmclInit on a small ring-with-chords graph, 4 iterations; every row sums to 1 and the
   // loop equals 4 single steps
   std::vector<int> er, ec; std::vector<double> ev;

@@ -144,6 +144,11 @@ def o_equal_partition64(prefix, parts):
     return ends
 
 
+def o_set_topk(k):
+    """Opt-in top-k of the checker's rMCL epilogue (0 = off); mirrors b200_set_topk."""
+    oracle().oracle_set_topk(int(k))
+
+
 def o_chaos(m):
     return float(oracle().oracle_chaos(_i(m.I), _d(m.V), m.rows))
 

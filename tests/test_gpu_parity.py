@@ -352,6 +352,19 @@ def test_sharded_loop_two_ranks_nccl():
         assert out.returncode == 0 and "parity with the checker: OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
+def test_cost_prefix_is_products_plus_a_charge_per_heavy_row(gpu):
+    """b200_cost_prefix (the footprint-style cost the multi-GPU cuts balance): products, plus the
+    charge for every row with more than 512 products; charge 0 is the flops prefix itself."""
+    A = gpu.synth_rmat(11, 16, 3, True)
+    dA = A.toGpuCSR()
+    flops = gpu.flops_prefix(dA, dA)
+    assert np.array_equal(gpu.cost_prefix(dA, dA, 0), flops)
+    per = np.diff(flops)
+    want = np.concatenate([[0], np.cumsum(per + 1000 * (per > 512))])
+    assert np.array_equal(gpu.cost_prefix(dA, dA, 1000), want) and (per > 512).sum() > 0
+    dA.deviceDispose()
+
+
 def test_device_partition_matches_host_partition(gpu):
     """The sharded loop finds its cut points on the device; same arithmetic as
     arrayEqualPartition64 (util.cc:123-135): a 1-rank and the tiled path exercise it; here the
@@ -532,7 +545,7 @@ def test_cpp_host_layer(gpu, tmp_path):
                            "-L" + lib, "-lb200spgemm", "-Wl,-rpath," + lib])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "Diffs" not in out.stdout, out.stdout + out.stderr
-    assert out.stdout.count("Same") == 9
+    assert out.stdout.count("Same") == 11
 
 
 def test_baseline_config_c1_nrmcl_rmat16(gpu):
@@ -653,3 +666,98 @@ def test_error_behaviour(gpu):
     ok = gpu.gpuSpMMWrapper(dA, dA)                         # still works afterwards
     assert ok.nnz > 0
     ok.deviceDispose(); dA.deviceDispose(); dB.deviceDispose()
+
+
+def test_cpp_driver_same_and_diffs(gpu, tmp_path):
+    """The C++ driver in the shape of nrmcl.cc, run as a user would: nrmcl_b200.x --input FILE
+    -r B200 --maxIters 5 --expect FILE prints the reference driver's verdict line (nrmcl.cc:27-32):
+    Same against the checker's Mt, Diffs against a perturbed one."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sparse_matrix_with_flops_b200", "nrmcl_b200.x")
+    assert os.path.exists(exe), "built by sparse_matrix_with_flops_b200/csrc/Makefile"
+    rng = np.random.default_rng(5)
+    n, m = 600, 6000
+    key = np.unique(rng.integers(0, n, m).astype(np.int64) * n + rng.integers(0, n, m))
+    key = np.unique(np.concatenate([key, (key % n) * n + key // n]))          # symmetric, no repeated pairs
+    er, ec = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    edges = tmp_path / "g.snap"
+    with open(edges, "w") as f:
+        f.write("# synthetic\n%d %d\n" % (n, len(er)))
+        for a, b in zip(er, ec):
+            f.write("%d %d\n" % (a, b))
+    # readSNAPFile's default is the transposed read (row = to, col = from; nlibs/COO.cc:142-148)
+    M0 = ol.o_rmcl_init(ec, er, n)
+    want, _, _ = ol.o_rmcl_iter(M0, M0, 5)
+    ol.o_make_ordered(want)
+
+    def write(path, Mx, bump=None):
+        with open(path, "w") as f:
+            f.write("%d %d %d\n" % (Mx.rows, Mx.cols, Mx.nnz))
+            rows = np.repeat(np.arange(Mx.rows), np.diff(Mx.I))
+            for k, (r, c, v) in enumerate(zip(rows, Mx.J, Mx.V)):
+                f.write("%d %d %.17g\n" % (r, c, v * (1 + 1e-9) if k == bump else v))
+    good, bad, out = tmp_path / "want.txt", tmp_path / "bad.txt", tmp_path / "got.txt"
+    write(good, want)
+    write(bad, want, bump=want.nnz // 2)
+    run = lambda exp: subprocess.run([exe, "--input", str(edges), "-r", "B200", "--maxIters", "5", "--expect", str(exp),
+                                      "--output", str(out)], capture_output=True, text=True, timeout=300)
+    r = run(good)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == "Same", r.stdout[-1500:] + r.stderr[-1500:]
+    assert "iters 5" in r.stdout and open(out).readline().split() == [str(n), str(n), str(want.nnz)]
+    r = run(bad)
+    assert r.returncode == 1 and r.stdout.strip().splitlines()[-1] == "Diffs", r.stdout[-1500:]
+
+
+@pytest.mark.parametrize("k", [1, 3, 12, 100000])
+@pytest.mark.parametrize("name,make", [SYNTH[0], SYNTH[5], HEAVY[2]])
+def test_topk_pruning_matches_the_checker(gpu, name, make, k, b200_options):
+    """Opt-in top-k (b200_set_topk): same rule as the checker's — the k largest entries above
+    the threshold, ties by ascending column — in the hash bins and in the bitmap bin; a k larger
+    than any row changes nothing.  Off again afterwards (parity runs use the threshold alone).
+    A rule that ranks VALUES needs the same values on both sides: these graphs are full of
+    exactly equal entries (1 / rowcount products), and a heavy row accumulated with fp64 RED can
+    differ from the reference in the last bit, which would break such a tie the other way — so
+    the heavy rows run in the bit-exact ordered mode here (B200_DETERMINISTIC)."""
+    b200_options(B200_DETERMINISTIC=1)
+    A = make(gpu)
+    try:
+        ol.o_set_topk(k)
+        gpu.set_topk(k)
+        want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+        step = A.staticOmpRmclOneStep(A)
+        step.makeOrdered()
+        assert np.diff(want1.I).max() <= k
+        ol.assert_same(M_of(step), want1, TOL, "%s top-%d step" % (name, k))
+        want, _, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 5)
+        ol.o_make_ordered(want)
+        Mt, _, hist = gpu.gpuRmclIter(5, A, A)
+        ol.assert_same(M_of(Mt), want, TOL, "%s top-%d loop" % (name, k))
+    finally:
+        ol.o_set_topk(0)
+        gpu.set_topk(0)
+    if k == 100000:
+        plain = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+        ol.assert_same(want1, plain, 0.0, "a k above every row length is the plain rule")
+
+
+@pytest.mark.parametrize("c", [2, 3, 7])
+def test_device_pcsr_column_striped_product(gpu, c):
+    """PCSR on the device (nlibs/PCSR.cc:3-56): the stripes equal the checker's split exactly,
+    and A x PCSR(B), stripe by stripe and glued back, equals the plain product
+    (correctTests/pcsrTest.cc)."""
+    A = random_csr(gpu, 700, 900, 0.02, 3)
+    B = gpu.synth_rmat(10, 16, 4, True)          # 1024 columns, hub rows
+    A = random_csr(gpu, 700, B.rows, 0.02, 3)
+    dA, dB = A.toGpuCSR(), B.toGpuCSR()
+    P = gpu.DevicePCSR(dB, c)
+    bp, rp, J, V = ol.o_pcsr_split(M_of(B), c)
+    assert P.stride == (B.cols + c - 1) // c and len(P.blocks) == c
+    for b, blk in enumerate(P.blocks):
+        h = blk.toCpuCSR()
+        assert np.array_equal(h.rowPtr, rp[b]) and np.array_equal(h.colInd, J[bp[b]:bp[b + 1]])
+        assert np.array_equal(h.values, V[bp[b]:bp[b + 1]])
+    dC = P.leftMultiply(dA)
+    got = M_of(dC.toCpuCSR())
+    ol.assert_same(got, want_spgemm(A, B), TOL, "PCSR product, c=%d" % c)
+    dC.deviceDispose(); P.dispose(); dA.deviceDispose(); dB.deviceDispose()

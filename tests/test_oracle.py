@@ -108,3 +108,24 @@ def test_oracle_equals_reference_on_fresh_inputs(smf, seed, scale, ef, sym):
     assert np.array_equal(pre, ol.r_flops_prefix(A, A))
     for parts in (2, 5, 8):
         assert np.array_equal(ol.o_equal_partition64(pre, parts), ol.r_equal_partition64(pre, parts))
+
+
+def test_topk_rule_of_the_checker():
+    """Opt-in top-k (not in the reference): of the entries that pass the threshold the k largest
+    stay, equal values ranked by ascending column; k = 0 leaves the reference's rule untouched."""
+    cols = np.array([7, 3, 9, 1, 5, 8], dtype=np.int32)
+    vals = np.sqrt(np.array([0.30, 0.20, 0.20, 0.20, 0.05, 0.05]))
+    base = ol.o_row_epilogue(cols.copy(), vals.copy())
+    try:
+        ol.o_set_topk(3)
+        c3, v3 = ol.o_row_epilogue(cols.copy(), vals.copy())
+        # 0.30 and two of the three 0.20s: the ones in columns 1 and 3 (ascending column), storage order kept
+        assert list(c3) == [7, 3, 1] and np.allclose(v3, np.array([0.3, 0.2, 0.2]) / 0.7)
+        ol.o_set_topk(1)
+        c1, v1 = ol.o_row_epilogue(cols.copy(), vals.copy())
+        assert list(c1) == [7] and v1[0] == 1.0
+        ol.o_set_topk(100)
+        c9, v9 = ol.o_row_epilogue(cols.copy(), vals.copy())
+        assert list(c9) == list(base[0]) and np.array_equal(v9, base[1])
+    finally:
+        ol.o_set_topk(0)
