@@ -49,6 +49,7 @@ constexpr int SB_W1K = 2;     // P <= 512
 constexpr int SB_W4K = 3;     // P <= 2048
 constexpr int SB_W16K = 4;    // P <= 8192
 constexpr int SB_BITMAP = 5;  // larger
+constexpr int SB_ESC = 6;     // rMCL only: sorted on chip (esc.cuh); no symbolic pass, nnz bound = P
 // numeric bins (by nnz(C_i))
 constexpr int NB_NONE = 0;    // empty row
 constexpr int NB_W64 = 1;
@@ -57,13 +58,17 @@ constexpr int NB_W1K = 3;
 constexpr int NB_W2K = 4;
 constexpr int NB_BITMAP = 5;
 constexpr int NB_W128 = 6;   // nnz(C_i) in (64, 128]: e.g. every interior row of a 27-point stencil
+constexpr int NB_ESC2K = 7;  // rMCL rows sorted on chip: <= 2048 products from <= 256 A entries
+constexpr int NB_ESC8K = 8;  // ... <= 8192 products from <= 512 A entries
+constexpr int ESC_MIN_P = 1024;  // below: the small warp tables (first-touch order, bit-identical row sums) serve well
 
 // `big_from`: rows above this size go to the bitmap bin.  When the column bitmap of B fits in
 // shared memory it is the cheapest accumulator index for every row past the small warp tables
 // (its per-row cost is O(n/64) words to clear), so the cut is low (P > 512, nnz(C_i) > 256);
 // otherwise the larger warp tables take the rows up to 8192 products / 2048 entries.
-__host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_from) {
+__host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_from, long long esc_max = 0) {
   if (P == 0 || annz <= 1) return SB_NONE;
+  if (P > ESC_MIN_P && P <= esc_max && ((P <= 2048 && annz <= 256) || annz <= 512)) return SB_ESC;
   if (P <= 128) return SB_W256;
   if (P <= 512) return SB_W1K;
   if (P > big_from) return SB_BITMAP;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(256)
 k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
             const int64_t* __restrict__ Brp, int row_lo, int m, long long big_from,
             long long* __restrict__ flops, unsigned char* __restrict__ sbin,
-            int* __restrict__ rownnz) {
+            int* __restrict__ rownnz, long long esc_max = 0) {
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(gt >> 3), sub = (int)(gt & 7);
   const bool live = i < m;
@@ -226,16 +231,22 @@ k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
   for (int o = 4; o > 0; o >>= 1) f += shfl64_xor(f, o);
   if (!live || sub != 0) return;
   flops[i] = f;
-  const int b = sym_bin_of(f, (int)(a1 - a0), big_from);
+  const int b = sym_bin_of(f, (int)(a1 - a0), big_from, esc_max);
   sbin[i] = (unsigned char)b;
-  if (b == SB_NONE) rownnz[i] = (int)f;  // 0, or the length of the single B row
+  // 0, or the length of the single B row; for a row sorted on chip its products BOUND its entries
+  if (b == SB_NONE || b == SB_ESC) rownnz[i] = (int)f;
 }
 
 __global__ void __launch_bounds__(256)
 k_num_bins(const int* __restrict__ rownnz, const long long* __restrict__ flops, int m, int big_from,
-           long long light_p, long long light2k_p, unsigned char* __restrict__ nbin) {
+           long long light_p, long long light2k_p, const unsigned char* __restrict__ sbin,
+           const int64_t* __restrict__ Arp, int row_lo, unsigned char* __restrict__ nbin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p, light2k_p);
+  if (i >= m) return;
+  // (the 2 K kernel holds at most 256 A entries, the 8 K one 512: see sym_bin_of)
+  if (sbin[i] == SB_ESC)
+    nbin[i] = (unsigned char)((flops[i] <= 2048 && Arp[row_lo + i + 1] - Arp[row_lo + i] <= 256) ? NB_ESC2K : NB_ESC8K);
+  else nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p, light2k_p);
 }
 
 // histogram of bin ids (<= 16 bins)
@@ -1811,6 +1822,7 @@ k_gather_rows(int m, const long long* __restrict__ row_off, const int64_t* __res
 }
 
 #include "ranges.cuh"
+#include "esc.cuh"
 
 struct IntToI64 {
   __host__ __device__ __forceinline__ long long operator()(const int& x) const { return (long long)x; }
@@ -1883,6 +1895,7 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_ARENA_ENTRIES")) t->arena_entries = atoll(e);
   if (const char* e = getenv("B200_ROW_CHARGE")) t->row_charge = std::max(0LL, atoll(e));
   t->deterministic = flag("B200_DETERMINISTIC");
+  if (const char* e = getenv("B200_ESC")) t->esc = atoi(e) ? 1 : 0;
   if (t->deterministic) t->on_chip = true;
 }
 
@@ -2146,6 +2159,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   const size_t unit_dyn = (size_t)unit_pool * UNIT_WARPS;
   const int item_pool = unit_pool - 16;
 
+  // mid-size rows of an rMCL step are sorted on chip (esc.cuh), without a symbolic pass
+  // — in very wide matrices, where a bitmap row costs one work item per 512 K-column part and the
+  // large warp tables run at 4 warps per SM (measured on the 4 M-vertex planted-partition graph:
+  // light iterate 873 -> 265 ms, heavy iterate 3136 -> 1342 ms); below ~1 M columns the bitmap
+  // path is the faster one (R-MAT scale 18 loop: 215 ms against 237), so it stays.  B200_ESC=0 / 1
+  // forces the choice.
+  const bool use_esc = c.tun.esc < 0 ? nparts > 2 : c.tun.esc > 0;
+  const long long esc_max = (mode == MODE_RMCL && use_esc) ? 8192 : 0;
+
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
   unsigned char* d_bin = nullptr;
@@ -2157,7 +2179,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   B200_CUDA(T.alloc(&d_P, 2));
   if (m > 0) {
     k_row_flops<<<(unsigned)(((long long)m * 8 + 255) / 256), 256, 0, st>>>(
-        A.rowptr, A.col, B.rowptr, row_lo, m, sym_big_from, d_flops, d_bin, d_cnt);
+        A.rowptr, A.col, B.rowptr, row_lo, m, sym_big_from, d_flops, d_bin, d_cnt, esc_max);
     ++launches;
   }
   {
@@ -2383,7 +2405,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (m > 0) {
     const long long light_p = c.tun.light_p >= 0 ? c.tun.light_p : 2560LL * std::max(1, nparts / 2);
     k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p,
-                                                nparts > 2 ? light_p : 0, d_nbin);
+                                                nparts > 2 ? light_p : 0, d_bin, A.rowptr, row_lo, d_nbin);
     ++launches;
   }
   B200_CUDA(cudaMemsetAsync(d_cnt + m, 0, sizeof(int), st));
@@ -2420,6 +2442,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int* d_kept = nullptr;
   int* d_scr_col = nullptr;
   double* d_scr_val = nullptr;
+  unsigned long long* d_esc = nullptr;  // [0] true unpruned entries of the rows sorted on chip
+  int* d_escwork = nullptr;
   long long scr_stride = 0;
   if (mode == MODE_SPGEMM) {
     C->rowptr = d_urp;
@@ -2505,6 +2529,30 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if ((rc = launch_num_warp(NB_W256, k_num_warp<256, true>, 256, 8))) return rc;
     if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, true>, 1024, 8))) return rc;
     if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, true>, 2048, 4))) return rc;
+    if (nb.cnt[NB_ESC2K] || nb.cnt[NB_ESC8K]) {
+      B200_CUDA(T.alloc(&d_esc, 2));
+      B200_CUDA(cudaMemsetAsync(d_esc, 0, 2 * sizeof(unsigned long long), st));
+      B200_CUDA(T.alloc(&d_escwork, 2));
+      B200_CUDA(cudaMemsetAsync(d_escwork, 0, 2 * sizeof(int), st));
+      int col_bits = 1;
+      while (col_bits < 32 && (1ll << col_bits) < (long long)n) ++col_bits;
+#define LAUNCH_ESC(BIN, BTE, IPTE, SLOT)                                                        \
+  if (nb.cnt[BIN]) {                                                                            \
+    const size_t esm = sizeof(EscSmem<BTE, IPTE>);                                              \
+    if ((rc = set_smem(k_esc_rmcl<BTE, IPTE>, esm))) return rc;                                 \
+    const int per_sm = std::max(1, (int)std::min<size_t>(2048 / BTE, (c.smem_optin + 1024) / (esm + 1024))); \
+    const int egrid = std::min(nb.cnt[BIN], per_sm * c.sm_count);                               \
+    tick(32 + 2 * BIN);                                                                         \
+    k_esc_rmcl<BTE, IPTE><<<egrid, BTE, esm, st>>>(nb.d_list + nb.off[BIN], nb.cnt[BIN], row_lo, \
+        A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, d_urp, col_bits, ro, d_esc, d_escwork + SLOT); \
+    tick(32 + 2 * BIN + 1);                                                                     \
+    num_timed[BIN] = true;                                                                      \
+    ++launches;                                                                                 \
+  }
+      LAUNCH_ESC(NB_ESC2K, 256, 8, 0)
+      LAUNCH_ESC(NB_ESC8K, 512, 16, 1)
+#undef LAUNCH_ESC
+    }
   }
   if (nbig_num) {
     const int grid = std::min(nbig_num, c.sm_count);
@@ -2660,6 +2708,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
 
   // ---- 6. rMCL: scan kept counts, gather arena -> final CSR
   long long nnz_out = unpruned;
+  unsigned long long h_esc_true = 0;
   if (mode == MODE_RMCL) {
     B200_CUDA(cudaMemsetAsync(d_kept + m, 0, sizeof(int), st));
     B200_CUDA(T.alloc(&C->rowptr, (size_t)m + 1));
@@ -2673,6 +2722,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ++launches;
     unsigned long long h_cur[2] = {0, 0};
     long long h_kept_total = 0;
+    if (d_esc) B200_CUDA(d2h_small(&h_esc_true, d_esc, sizeof(unsigned long long), st));
     B200_CUDA(d2h_small(h_cur, d_cursor, 2 * sizeof(unsigned long long), st));
     B200_CUDA(d2h_small(&h_kept_total, C->rowptr + m, sizeof(long long), st));
     B200_CUDA(sync_fetch(st));
@@ -2729,7 +2779,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->ms_other = t23 + t45;
     stats->products = h_tot[1];
     stats->nnz_out = nnz_out;
+    // (rows sorted on chip reserved their products as a bound: report what they really held)
     stats->nnz_unpruned = unpruned;
+    if (d_esc) {
+      const long long bound = (long long)h_agg[48 + NB_ESC2K * 3 + 0] + (long long)h_agg[48 + NB_ESC8K * 3 + 0];
+      stats->nnz_unpruned = unpruned - bound + (long long)h_esc_true;
+    }
     stats->launches = launches;
     stats->part_kernel = use_parts ? 1 : 0;
     stats->part_count = nparts;

@@ -761,3 +761,30 @@ def test_device_pcsr_column_striped_product(gpu, c):
     got = M_of(dC.toCpuCSR())
     ol.assert_same(got, want_spgemm(A, B), TOL, "PCSR product, c=%d" % c)
     dC.deviceDispose(); P.dispose(); dA.deviceDispose(); dB.deviceDispose()
+
+
+@pytest.mark.parametrize("name,make", [SYNTH[0], SYNTH[2], HEAVY[0], HEAVY[1]])
+def test_rmcl_rows_sorted_on_chip(gpu, name, make, b200_options):
+    """Mid-size rows of an rMCL step (1024 < products <= 8192) expanded, sorted by column and
+    summed in A-entry order on chip (esc.cuh; the default in matrices wider than 1 M columns,
+    forced here): same step and same loop as the checker, and the pre-prune entry count the
+    library reports for them is exact although their arena slices are reserved by products."""
+    A = make(gpu)
+    dG = A.toGpuCSR()
+    b200_options(B200_ESC=0)
+    ref_step, ch0, st0 = gpu.gpuRmclOneStep(dG, dG, want_stats=True)
+    b200_options(B200_ESC=1)
+    esc_step, ch1, st1 = gpu.gpuRmclOneStep(dG, dG, want_stats=True)
+    assert st0["bins_rows"][7] + st0["bins_rows"][8] == 0 and st1["bins_rows"][7] + st1["bins_rows"][8] > 0
+    assert st1["nnz_unpruned"] == st0["nnz_unpruned"] and st1["products"] == st0["products"]
+    a, b = ref_step.toCpuCSR().makeOrdered(), esc_step.toCpuCSR().makeOrdered()
+    ref_step.deviceDispose(); esc_step.deviceDispose(); dG.deviceDispose()
+    want1 = ol.o_make_ordered(ol.o_rmcl_onestep(M_of(A), M_of(A)))
+    ol.assert_same(M_of(b), want1, TOL, name + " step, rows sorted on chip")
+    ol.assert_same(M_of(b), M_of(a), TOL, name + " both paths")
+    assert abs(ch1 - ol.o_chaos(want1)) <= 1e-12
+    want, _, hist_w = ol.o_rmcl_iter(M_of(A), M_of(A), 6)
+    ol.o_make_ordered(want)
+    Mt, _, hist = gpu.gpuRmclIter(6, A, A)
+    ol.assert_same(M_of(Mt), want, TOL, name + " loop, rows sorted on chip")
+    assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
