@@ -76,9 +76,11 @@ L2_BYTES = 126 * 1024 * 1024
 
 # numeric / symbolic bin names (sparse_matrix_with_flops_b200/csrc/spgemm.cu)
 SYM_KERNELS = {1: "k_sym_warp<256>", 2: "k_sym_warp<1024>", 3: "k_sym_warp<4096>",
-               4: "k_sym_warp<16384>", 5: "k_sym_bitmap"}
+               4: "k_sym_warp<16384>", 5: "k_sym_bitmap",
+               6: "k_esc<256,8> (expand/sort/compress, SpGEMM)", 7: "k_esc<512,16> (expand/sort/compress, SpGEMM)"}
 NUM_KERNELS = {1: "k_num_warp<64>", 6: "k_num_warp<128>", 2: "k_num_warp<256>", 3: "k_num_warp<1024>",
-               4: "k_num_warp<2048>", 5: "k_num_bitmap", 7: "k_esc_rmcl<256,8>", 8: "k_esc_rmcl<512,16>"}
+               4: "k_num_warp<2048>", 5: "k_num_bitmap", 7: "k_esc<256,8> (rMCL) / k_esc_gather",
+               8: "k_esc<512,16> (rMCL) / k_esc_gather"}
 
 
 def parse_args():

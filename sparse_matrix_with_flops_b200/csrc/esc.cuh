@@ -38,13 +38,17 @@ struct EscSmem {
   double redd[BT / 32 + 1];
 };
 
-template <int BT, int IPT>
+// RMCL = false (plain SpGEMM): the same expand / sort / compress runs in the SYMBOLIC phase — it
+// leaves the finished row (ascending columns) in the arena slice reserved by the row's products
+// and its length in rownnz; after the row offsets of C are known, k_esc_gather moves it there.
+template <int BT, int IPT, bool RMCL>
 __global__ void __launch_bounds__(BT)
 k_esc_rmcl(const int* __restrict__ list, int count, int row_lo, const int64_t* __restrict__ Arp,
            const int* __restrict__ Acol, const double* __restrict__ Aval,
            const int64_t* __restrict__ Brp, const int* __restrict__ Bcol,
            const double* __restrict__ Bval, const int64_t* __restrict__ Crp, int col_bits, RmclOut ro,
-           unsigned long long* __restrict__ true_unpruned, int* __restrict__ work_counter) {
+           unsigned long long* __restrict__ true_unpruned, int* __restrict__ work_counter,
+           int* __restrict__ rownnz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EscSmem<BT, IPT>& sm = *reinterpret_cast<EscSmem<BT, IPT>*>(smem_raw);
   __shared__ int s_idx;
@@ -163,6 +167,15 @@ k_esc_rmcl(const int* __restrict__ list, int count, int row_lo, const int64_t* _
         if (ocol[k] >= 0) { sm.u.row.col[hbase + h] = ocol[k]; sm.u.row.val[hbase + h] = oval[k]; ++h; }
     }
     __syncthreads();
+    if (!RMCL) {
+      const long long off = (long long)Crp[i];   // (here: the row's slice of the arena)
+      for (int k = threadIdx.x; k < cnt; k += BT) {
+        ro.arena_col[off + k] = sm.u.row.col[k];
+        ro.arena_val[off + k] = sm.u.row.val[k];
+      }
+      if (threadIdx.x == 0) rownnz[i] = cnt;
+      continue;
+    }
     // ---- rMCL epilogue over the row in shared memory (ascending columns; nlibs/tools/util.cc:4-69)
     int* rcol = sm.u.row.col;
     double* acc = sm.u.row.val;
@@ -225,4 +238,17 @@ k_esc_rmcl(const int* __restrict__ list, int count, int row_lo, const int64_t* _
       atomicAdd(true_unpruned, (unsigned long long)cnt);
     }
   }
+}
+
+// SpGEMM: rows finished in the arena by k_esc_rmcl<.., false> move to their place in C
+__global__ void __launch_bounds__(256)
+k_esc_gather(const int* __restrict__ list, int count, const int64_t* __restrict__ escoff,
+             const int64_t* __restrict__ Crp, const int* __restrict__ arena_col,
+             const double* __restrict__ arena_val, int* __restrict__ Ccol, double* __restrict__ Cval) {
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const int i = list[w];
+  const int64_t s = escoff[i], o = Crp[i];
+  const int k = (int)(Crp[i + 1] - o);
+  for (int t = lane; t < k; t += 32) { Ccol[o + t] = arena_col[s + t]; Cval[o + t] = arena_val[s + t]; }
 }

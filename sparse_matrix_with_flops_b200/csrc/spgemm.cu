@@ -49,7 +49,9 @@ constexpr int SB_W1K = 2;     // P <= 512
 constexpr int SB_W4K = 3;     // P <= 2048
 constexpr int SB_W16K = 4;    // P <= 8192
 constexpr int SB_BITMAP = 5;  // larger
-constexpr int SB_ESC = 6;     // rMCL only: sorted on chip (esc.cuh); no symbolic pass, nnz bound = P
+constexpr int SB_ESC2K = 6;   // sorted on chip (esc.cuh): <= 2048 products from <= 256 A entries
+constexpr int SB_ESC8K = 7;   // ... <= 8192 products from <= 512 A entries.  No symbolic hashing: the
+                              // row's products bound its entries
 // numeric bins (by nnz(C_i))
 constexpr int NB_NONE = 0;    // empty row
 constexpr int NB_W64 = 1;
@@ -68,7 +70,10 @@ constexpr int ESC_MIN_P = 1024;  // below: the small warp tables (first-touch or
 // otherwise the larger warp tables take the rows up to 8192 products / 2048 entries.
 __host__ __device__ inline int sym_bin_of(long long P, int annz, long long big_from, long long esc_max = 0) {
   if (P == 0 || annz <= 1) return SB_NONE;
-  if (P > ESC_MIN_P && P <= esc_max && ((P <= 2048 && annz <= 256) || annz <= 512)) return SB_ESC;
+  if (P > ESC_MIN_P && P <= esc_max) {
+    if (P <= 2048 && annz <= 256) return SB_ESC2K;
+    if (annz <= 512) return SB_ESC8K;
+  }
   if (P <= 128) return SB_W256;
   if (P <= 512) return SB_W1K;
   if (P > big_from) return SB_BITMAP;
@@ -234,7 +239,7 @@ k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
   const int b = sym_bin_of(f, (int)(a1 - a0), big_from, esc_max);
   sbin[i] = (unsigned char)b;
   // 0, or the length of the single B row; for a row sorted on chip its products BOUND its entries
-  if (b == SB_NONE || b == SB_ESC) rownnz[i] = (int)f;
+  if (b == SB_NONE || b == SB_ESC2K || b == SB_ESC8K) rownnz[i] = (int)f;
 }
 
 __global__ void __launch_bounds__(256)
@@ -243,10 +248,17 @@ k_num_bins(const int* __restrict__ rownnz, const long long* __restrict__ flops, 
            const int64_t* __restrict__ Arp, int row_lo, unsigned char* __restrict__ nbin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  // (the 2 K kernel holds at most 256 A entries, the 8 K one 512: see sym_bin_of)
-  if (sbin[i] == SB_ESC)
-    nbin[i] = (unsigned char)((flops[i] <= 2048 && Arp[row_lo + i + 1] - Arp[row_lo + i] <= 256) ? NB_ESC2K : NB_ESC8K);
+  if (sbin[i] == SB_ESC2K) nbin[i] = (unsigned char)NB_ESC2K;
+  else if (sbin[i] == SB_ESC8K) nbin[i] = (unsigned char)NB_ESC8K;
   else nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p, light2k_p);
+}
+
+// arena length of a row finished on chip in the symbolic phase (SpGEMM, esc.cuh): its products
+__global__ void __launch_bounds__(256)
+k_esc_len(const unsigned char* __restrict__ sbin, const long long* __restrict__ flops, int m,
+          long long* __restrict__ len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= m) len[i] = (i < m && (sbin[i] == 6 || sbin[i] == 7)) ? flops[i] : 0;
 }
 
 // histogram of bin ids (<= 16 bins)
@@ -2166,7 +2178,38 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   // path is the faster one (R-MAT scale 18 loop: 215 ms against 237), so it stays.  B200_ESC=0 / 1
   // forces the choice.
   const bool use_esc = c.tun.esc < 0 ? nparts > 2 : c.tun.esc > 0;
-  const long long esc_max = (mode == MODE_RMCL && use_esc) ? 8192 : 0;
+  const long long esc_max = use_esc ? 8192 : 0;
+
+  // arena of unpruned rows (rMCL) / of the rows finished on chip before C exists (SpGEMM, esc.cuh)
+  auto ensure_arena = [&](size_t need_entries) -> int {
+    const size_t unpruned = need_entries;
+    if (c.arena_cap < (size_t)unpruned) {
+      B200_CUDA(sync_fetch(st));
+      // head-room: an rMCL loop alternates between a few sizes, and re-allocating tens of GB
+      // costs ~1 s; grow by at least 2x the old capacity (falls back to the exact size below)
+      const size_t old_cap = c.arena_cap;
+      const size_t want = std::max((size_t)unpruned + (size_t)unpruned / 8 + 1, 2 * old_cap);
+      if (c.arena_col) { cudaFree(c.arena_col); cudaFree(c.arena_val); }
+      c.arena_col = nullptr; c.arena_val = nullptr; c.arena_cap = 0;
+      size_t got = want;
+      if (cudaMalloc((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
+          cudaMalloc((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
+        got = (size_t)unpruned + 1;  // without the head-room, and with the pool trimmed if needed
+        if (malloc_with_trim((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
+            malloc_with_trim((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
+          if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
+          c.arena_val = nullptr;
+          set_error("out of device memory for the rMCL arena (unpruned product of this row block); "
+                    "shard the rows over more GPUs or call the *_rows entry points on smaller blocks");
+          return B200_ERR_CUDA;
+        }
+      }
+      c.arena_cap = got;
+    }
+    return B200_OK;
+  };
 
   // ---- 1. flops analysis + symbolic binning
   long long* d_flops = nullptr;
@@ -2267,6 +2310,55 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if ((rc = launch_sym_warp(SB_W1K, k_sym_warp<1024>, 1024, 8, k_sym_warp<1024>, 0, 0))) return rc;
   if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8, k_sym_warp<1024>, 1024, 0))) return rc;
   if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3, k_sym_warp<4096>, 4096, 1))) return rc;
+
+  // rows sorted on chip (esc.cuh), plain SpGEMM: computed HERE, once — the finished row waits in
+  // the arena, its length goes into the row counts like any symbolic result
+  int64_t* d_escoff = nullptr;
+  int* d_escwork = nullptr;
+  int esc_col_bits = 1;
+  while (esc_col_bits < 32 && (1ll << esc_col_bits) < (long long)n) ++esc_col_bits;
+#define LAUNCH_ESC(RM, LIST, COUNT, BTE, IPTE, SLOT, OFFS, ROUT, NNZ, TIMER)                    \
+  if (COUNT) {                                                                                  \
+    const size_t esm = sizeof(EscSmem<BTE, IPTE>);                                              \
+    if ((rc = set_smem(k_esc_rmcl<BTE, IPTE, RM>, esm))) return rc;                             \
+    const int per_sm = std::max(1, (int)std::min<size_t>(2048 / BTE, (c.smem_optin + 1024) / (esm + 1024))); \
+    const int egrid = std::min((int)(COUNT), per_sm * c.sm_count);                              \
+    tick(TIMER);                                                                                \
+    k_esc_rmcl<BTE, IPTE, RM><<<egrid, BTE, esm, st>>>(LIST, COUNT, row_lo, A.rowptr, A.col, A.val, \
+        B.rowptr, B.col, B.val, OFFS, esc_col_bits, ROUT, d_esc, d_escwork + SLOT, NNZ);         \
+    tick(TIMER + 1);                                                                            \
+    ++launches;                                                                                 \
+  }
+  unsigned long long* d_esc = nullptr;  // [0] true unpruned entries of the rows sorted on chip
+  if (sb.cnt[SB_ESC2K] || sb.cnt[SB_ESC8K]) {
+    B200_CUDA(T.alloc(&d_esc, 2));
+    B200_CUDA(cudaMemsetAsync(d_esc, 0, 2 * sizeof(unsigned long long), st));
+    B200_CUDA(T.alloc(&d_escwork, 2));
+    B200_CUDA(cudaMemsetAsync(d_escwork, 0, 2 * sizeof(int), st));
+  }
+  if (mode == MODE_SPGEMM && (sb.cnt[SB_ESC2K] || sb.cnt[SB_ESC8K])) {
+    long long* d_len = nullptr;
+    B200_CUDA(T.alloc(&d_len, (size_t)m + 1));
+    B200_CUDA(T.alloc(&d_escoff, (size_t)m + 1));
+    k_esc_len<<<(m + 256) / 256, 256, 0, st>>>(d_bin, d_flops, m, d_len);
+    void* tmp = nullptr;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_len, (long long*)d_escoff, m + 1, st);
+    B200_CUDA(T.alloc((char**)&tmp, tb ? tb : 1));
+    cub::DeviceScan::ExclusiveSum(tmp, tb, d_len, (long long*)d_escoff, m + 1, st);
+    long long h_need = 0;
+    B200_CUDA(d2h_small(&h_need, d_escoff + m, sizeof(long long), st));
+    B200_CUDA(sync_fetch(st));
+    if ((rc = ensure_arena((size_t)h_need))) return rc;
+    RmclOut eo = {};
+    eo.arena_col = c.arena_col;
+    eo.arena_val = c.arena_val;
+    sym_timed[SB_ESC2K] = sb.cnt[SB_ESC2K] > 0;
+    sym_timed[SB_ESC8K] = sb.cnt[SB_ESC8K] > 0;
+    LAUNCH_ESC(false, sb.d_list + sb.off[SB_ESC2K], sb.cnt[SB_ESC2K], 256, 8, 0, d_escoff, eo, d_cnt, 2 * SB_ESC2K)
+    LAUNCH_ESC(false, sb.d_list + sb.off[SB_ESC8K], sb.cnt[SB_ESC8K], 512, 16, 1, d_escoff, eo, d_cnt, 2 * SB_ESC8K)
+    launches += 2;
+  }
 
   // large rows: bitmap
   unsigned long long* d_bmstore = nullptr;  // stored bitmaps of the symbolic bitmap bin
@@ -2442,8 +2534,6 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   int* d_kept = nullptr;
   int* d_scr_col = nullptr;
   double* d_scr_val = nullptr;
-  unsigned long long* d_esc = nullptr;  // [0] true unpruned entries of the rows sorted on chip
-  int* d_escwork = nullptr;
   long long scr_stride = 0;
   if (mode == MODE_SPGEMM) {
     C->rowptr = d_urp;
@@ -2452,31 +2542,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     B200_CUDA(T.alloc(&C->col, (size_t)unpruned));
     B200_CUDA(T.alloc(&C->val, (size_t)unpruned));
   } else {
-    if (c.arena_cap < (size_t)unpruned) {
-      B200_CUDA(sync_fetch(st));
-      // head-room: an rMCL loop alternates between a few sizes, and re-allocating tens of GB
-      // costs ~1 s; grow by at least 2x the old capacity (falls back to the exact size below)
-      const size_t old_cap = c.arena_cap;
-      const size_t want = std::max((size_t)unpruned + (size_t)unpruned / 8 + 1, 2 * old_cap);
-      if (c.arena_col) { cudaFree(c.arena_col); cudaFree(c.arena_val); }
-      c.arena_col = nullptr; c.arena_val = nullptr; c.arena_cap = 0;
-      size_t got = want;
-      if (cudaMalloc((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
-          cudaMalloc((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
-        if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
-        got = (size_t)unpruned + 1;  // without the head-room, and with the pool trimmed if needed
-        if (malloc_with_trim((void**)&c.arena_col, got * sizeof(int)) != cudaSuccess ||
-            malloc_with_trim((void**)&c.arena_val, got * sizeof(double)) != cudaSuccess) {
-          if (c.arena_col) { cudaFree(c.arena_col); c.arena_col = nullptr; }
-          c.arena_val = nullptr;
-          set_error("out of device memory for the rMCL arena (unpruned product of this row block); "
-                    "shard the rows over more GPUs or call the *_rows entry points on smaller blocks");
-          return B200_ERR_CUDA;
-        }
-      }
-      c.arena_cap = got;
-    }
+    if ((rc = ensure_arena((size_t)unpruned))) return rc;
     d_arena_col = c.arena_col;
     d_arena_val = c.arena_val;
     B200_CUDA(T.alloc(&d_cursor, 2));
@@ -2518,6 +2584,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     return B200_OK;
   };
   if (mode == MODE_SPGEMM) {
+    for (int bin : {NB_ESC2K, NB_ESC8K})
+      if (nb.cnt[bin]) {   // rows finished on chip during the symbolic phase: from the arena into C
+        tick(32 + 2 * bin);
+        k_esc_gather<<<(unsigned)(((long long)nb.cnt[bin] * 32 + 255) / 256), 256, 0, st>>>(
+            nb.d_list + nb.off[bin], nb.cnt[bin], d_escoff, d_urp, c.arena_col, c.arena_val, C->col, C->val);
+        tick(32 + 2 * bin + 1);
+        num_timed[bin] = true;
+        ++launches;
+      }
     if ((rc = launch_num_warp(NB_W64, k_num_warp<64, false>, 64, 8))) return rc;
     if ((rc = launch_num_warp(NB_W128, k_num_warp<128, false>, 128, 8))) return rc;
     if ((rc = launch_num_warp(NB_W256, k_num_warp<256, false>, 256, 8))) return rc;
@@ -2529,31 +2604,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     if ((rc = launch_num_warp(NB_W256, k_num_warp<256, true>, 256, 8))) return rc;
     if ((rc = launch_num_warp(NB_W1K, k_num_warp<1024, true>, 1024, 8))) return rc;
     if ((rc = launch_num_warp(NB_W2K, k_num_warp<2048, true>, 2048, 4))) return rc;
-    if (nb.cnt[NB_ESC2K] || nb.cnt[NB_ESC8K]) {
-      B200_CUDA(T.alloc(&d_esc, 2));
-      B200_CUDA(cudaMemsetAsync(d_esc, 0, 2 * sizeof(unsigned long long), st));
-      B200_CUDA(T.alloc(&d_escwork, 2));
-      B200_CUDA(cudaMemsetAsync(d_escwork, 0, 2 * sizeof(int), st));
-      int col_bits = 1;
-      while (col_bits < 32 && (1ll << col_bits) < (long long)n) ++col_bits;
-#define LAUNCH_ESC(BIN, BTE, IPTE, SLOT)                                                        \
-  if (nb.cnt[BIN]) {                                                                            \
-    const size_t esm = sizeof(EscSmem<BTE, IPTE>);                                              \
-    if ((rc = set_smem(k_esc_rmcl<BTE, IPTE>, esm))) return rc;                                 \
-    const int per_sm = std::max(1, (int)std::min<size_t>(2048 / BTE, (c.smem_optin + 1024) / (esm + 1024))); \
-    const int egrid = std::min(nb.cnt[BIN], per_sm * c.sm_count);                               \
-    tick(32 + 2 * BIN);                                                                         \
-    k_esc_rmcl<BTE, IPTE><<<egrid, BTE, esm, st>>>(nb.d_list + nb.off[BIN], nb.cnt[BIN], row_lo, \
-        A.rowptr, A.col, A.val, B.rowptr, B.col, B.val, d_urp, col_bits, ro, d_esc, d_escwork + SLOT); \
-    tick(32 + 2 * BIN + 1);                                                                     \
-    num_timed[BIN] = true;                                                                      \
-    ++launches;                                                                                 \
+    num_timed[NB_ESC2K] = nb.cnt[NB_ESC2K] > 0;
+    num_timed[NB_ESC8K] = nb.cnt[NB_ESC8K] > 0;
+    LAUNCH_ESC(true, nb.d_list + nb.off[NB_ESC2K], nb.cnt[NB_ESC2K], 256, 8, 0, d_urp, ro, nullptr, 32 + 2 * NB_ESC2K)
+    LAUNCH_ESC(true, nb.d_list + nb.off[NB_ESC8K], nb.cnt[NB_ESC8K], 512, 16, 1, d_urp, ro, nullptr, 32 + 2 * NB_ESC8K)
   }
-      LAUNCH_ESC(NB_ESC2K, 256, 8, 0)
-      LAUNCH_ESC(NB_ESC8K, 512, 16, 1)
 #undef LAUNCH_ESC
-    }
-  }
   if (nbig_num) {
     const int grid = std::min(nbig_num, c.sm_count);
     if (!num_smem && !d_gscr)
@@ -2781,7 +2837,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->nnz_out = nnz_out;
     // (rows sorted on chip reserved their products as a bound: report what they really held)
     stats->nnz_unpruned = unpruned;
-    if (d_esc) {
+    if (d_esc && mode == MODE_RMCL) {
       const long long bound = (long long)h_agg[48 + NB_ESC2K * 3 + 0] + (long long)h_agg[48 + NB_ESC8K * 3 + 0];
       stats->nnz_unpruned = unpruned - bound + (long long)h_esc_true;
     }

@@ -771,6 +771,15 @@ def test_rmcl_rows_sorted_on_chip(gpu, name, make, b200_options):
     library reports for them is exact although their arena slices are reserved by products."""
     A = make(gpu)
     dG = A.toGpuCSR()
+    # plain SpGEMM: the same rows are finished on chip during the symbolic phase and moved into C
+    b200_options(B200_ESC=1)
+    dC, stc = gpu.gpuSpMMWrapper(dG, dG, want_stats=True)
+    got = M_of(dC.toCpuCSR())
+    dC.deviceDispose()
+    assert stc["bins_rows"][7] + stc["bins_rows"][8] > 0
+    wantC = want_spgemm(A, A)
+    ol.assert_same(got, wantC, TOL, name + " SpGEMM, rows sorted on chip")
+    assert stc["nnz_out"] == wantC.nnz == stc["nnz_unpruned"]
     b200_options(B200_ESC=0)
     ref_step, ch0, st0 = gpu.gpuRmclOneStep(dG, dG, want_stats=True)
     b200_options(B200_ESC=1)
