@@ -657,6 +657,9 @@ def run_b200(args):
     if kind == "num":
         kb = kernel_bytes("num", st["bins_rows"][b], st["num_bin_products"][b], st["num_bin_nnzA"][b],
                           st["num_bin_nnzC"][b])
+    elif b in (6, 7):   # rows finished on chip in the symbolic phase: a numeric kernel in all but name
+        kb = kernel_bytes("num", st["sym_bin_rows"][b], st["sym_bin_products"][b], st["sym_bin_nnzA"][b],
+                          st["num_bin_nnzC"][b + 1])
     else:
         kb = kernel_bytes("sym", st["sym_bin_rows"][b], st["sym_bin_products"][b], st["sym_bin_nnzA"][b], 0)
     achieved = kb / (kms * 1e-3) / 1e9
@@ -698,7 +701,8 @@ def run_b200(args):
         dA.deviceDispose()
         dA = None
         try:
-            r = rmcl_measure(args, env, args.rmcl_leg, max(1, min(args.steps, 2)), 1, not args.no_cpu,
+            # (two warm-up loops: the first grows the arena and the memory pool to their working sizes)
+            r = rmcl_measure(args, env, args.rmcl_leg, max(1, min(args.steps, 2)), 2, not args.no_cpu,
                              not args.no_e2e)
             rmcl = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config",
                                       "roofline", "cpu_baseline", "e2e", "gpu_launches")}
