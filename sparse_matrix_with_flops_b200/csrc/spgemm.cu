@@ -27,9 +27,15 @@
 //    segments of the part (k_bsplit table) and reduced with fp64 RED into the row's final slice
 //    of C.val (order of additions not fixed: values agree to rounding, not bitwise);
 //  * rMCL: inflation, row max/sum, threshold, prune, normalise and the chaos term are fused
-//    behind the numeric row while it is still on chip (hash bins) or in a per-CTA scratch
-//    (bitmap bin); pruned rows go to a bump-allocated arena and are gathered into the final CSR
-//    after a scan of the kept counts, so the unpruned product is never materialised in CSR form.
+//    behind the numeric row while it is still on chip (hash bins, on-chip sort bin: only the kept
+//    entries leave the chip) or run in place over the row's arena slice (bitmap bin: the part
+//    kernel writes the unpruned row there first).  The arena is sized by the unpruned entries of
+//    the rows of ONE call; tiles.cu bounds it by running a step as consecutive row tiles.  Kept
+//    entries are gathered into the final CSR after a scan of the kept counts;
+//  * mid-size rows of matrices wider than two column parts: expanded, sorted by column and
+//    summed on chip (esc.cuh), no symbolic pass;
+//  * opt-in (B200_ON_CHIP / B200_DETERMINISTIC): heavy rows accumulated on chip in A-entry order
+//    (ranges.cuh) instead of with RED.
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <vector>
