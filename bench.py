@@ -80,7 +80,8 @@ SYM_KERNELS = {1: "k_sym_warp<256>", 2: "k_sym_warp<1024>", 3: "k_sym_warp<4096>
                6: "k_esc<256,8> (expand/sort/compress, SpGEMM)", 7: "k_esc<512,16> (expand/sort/compress, SpGEMM)"}
 NUM_KERNELS = {1: "k_num_warp<64>", 6: "k_num_warp<128>", 2: "k_num_warp<256>", 3: "k_num_warp<1024>",
                4: "k_num_warp<2048>", 5: "k_num_bitmap", 7: "k_esc<256,8> (rMCL) / k_esc_gather",
-               8: "k_esc<512,16> (rMCL) / k_esc_gather"}
+               8: "k_esc<512,16> (rMCL) / k_esc_gather", 9: "k_esc_gather (rows of k_num_warp_fused)"}
+FUSED_BIN = 9   # numeric bin of the rows k_num_warp_fused<128> finished in the symbolic phase
 
 
 def parse_args():
@@ -644,8 +645,11 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     cands = []
+    fused = st["bins_rows"][FUSED_BIN] > 0
     for b, nm in SYM_KERNELS.items():
         if acc["sym"][b] > 0:
+            if b == 3 and fused:   # (+ the symbolic retry of the rows that did not fit 128 columns)
+                nm = "k_num_warp_fused<128>"
             cands.append((acc["sym"][b] / args.steps, "sym", b, nm))
     for b, nm in NUM_KERNELS.items():
         if acc["num"][b] > 0:
@@ -660,6 +664,9 @@ def run_b200(args):
     elif b in (6, 7):   # rows finished on chip in the symbolic phase: a numeric kernel in all but name
         kb = kernel_bytes("num", st["sym_bin_rows"][b], st["sym_bin_products"][b], st["sym_bin_nnzA"][b],
                           st["num_bin_nnzC"][b + 1])
+    elif b == 3 and fused:   # likewise; the bytes of the rows it finished
+        kb = kernel_bytes("num", st["bins_rows"][FUSED_BIN], st["num_bin_products"][FUSED_BIN],
+                          st["num_bin_nnzA"][FUSED_BIN], st["num_bin_nnzC"][FUSED_BIN])
     else:
         kb = kernel_bytes("sym", st["sym_bin_rows"][b], st["sym_bin_products"][b], st["sym_bin_nnzA"][b], 0)
     achieved = kb / (kms * 1e-3) / 1e9

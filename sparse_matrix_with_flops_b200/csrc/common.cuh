@@ -43,6 +43,8 @@ struct Tunables {
                              // part kernel (global RED) on R-MAT scale 20, see DESIGN.md §3b
   int esc = -1;              // B200_ESC=0/1: rMCL rows of 1024..8192 products sorted on chip (esc.cuh) never /
                              // always; default (-1): in matrices wider than two column parts (> 1 M columns)
+  int fuse = -1;             // B200_FUSE=0/1: plain SpGEMM rows of 512..2048 products are first tried as 128-entry
+                             // numeric rows in the symbolic phase (k_num_warp_fused) never / always; default: always
   bool prof = false;         // B200_PROF: per-phase diagnostics on stderr
   int l2[5] = {2, 1, 0, 1, 0};  // B200_L2POL=acc,ocol,bgather,bmstore,demote (L2Prio values)
   long long sym_big_from = -1;  // B200_SYM_BIG_FROM, B200_NUM_BIG_FROM, B200_LIGHT_P: bin cuts (-1: default)

@@ -68,6 +68,8 @@ constexpr int NB_BITMAP = 5;
 constexpr int NB_W128 = 6;   // nnz(C_i) in (64, 128]: e.g. every interior row of a 27-point stencil
 constexpr int NB_ESC2K = 7;  // rMCL rows sorted on chip: <= 2048 products from <= 256 A entries
 constexpr int NB_ESC8K = 8;  // ... <= 8192 products from <= 512 A entries
+constexpr int NB_FUSED = 9;  // SpGEMM rows finished in the symbolic phase by k_num_warp_fused (<= 128 columns)
+constexpr int FUSED_CAP = 128;
 constexpr int ESC_MIN_P = 1024;  // below: the small warp tables (first-touch order, bit-identical row sums) serve well
 
 // `big_from`: rows above this size go to the bitmap bin.  When the column bitmap of B fits in
@@ -251,10 +253,12 @@ k_row_flops(const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
 __global__ void __launch_bounds__(256)
 k_num_bins(const int* __restrict__ rownnz, const long long* __restrict__ flops, int m, int big_from,
            long long light_p, long long light2k_p, const unsigned char* __restrict__ sbin,
-           const int64_t* __restrict__ Arp, int row_lo, unsigned char* __restrict__ nbin) {
+           const int64_t* __restrict__ Arp, int row_lo, const unsigned char* __restrict__ fused,
+           unsigned char* __restrict__ nbin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  if (sbin[i] == SB_ESC2K) nbin[i] = (unsigned char)NB_ESC2K;
+  if (fused && fused[i]) nbin[i] = (unsigned char)NB_FUSED;
+  else if (sbin[i] == SB_ESC2K) nbin[i] = (unsigned char)NB_ESC2K;
   else if (sbin[i] == SB_ESC8K) nbin[i] = (unsigned char)NB_ESC8K;
   else nbin[i] = (unsigned char)num_bin_of(rownnz[i], big_from, flops[i], light_p, light2k_p);
 }
@@ -600,6 +604,99 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
     if (ch < 0.0) ch = 0.0;
     atomicMax(ro.chaos_bits, (unsigned long long)__double_as_longlong(ch));
   }
+}
+
+
+// k_num_warp<CAP, false> run OPTIMISTICALLY in the symbolic phase (plain SpGEMM): for rows whose
+// products would need one of the large tables but whose columns may well fit the smallest ones —
+// every interior row of a 27-point stencil has 729 products and 125 columns — the numeric row is
+// built at once in a CAP-entry table.  If it fits, the sorted row waits in a fixed arena slot
+// (list position x CAP) for C's row offsets, its length goes into the row counts, and the row
+// needs neither a symbolic pass nor a second numeric one; if not, the row is handed to the
+// regular two-pass path (overflow_list).
+template <int CAP>
+__global__ void __launch_bounds__(256)
+k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
+                 const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
+                 const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
+                 const int* __restrict__ Bcol, const double* __restrict__ Bval,
+                 long long arena_base, int* __restrict__ arena_col, double* __restrict__ arena_val,
+                 int64_t* __restrict__ arena_off, int* __restrict__ rownnz,
+                 unsigned char* __restrict__ fused, int* __restrict__ overflow_list,
+                 int* __restrict__ overflow_count) {
+  constexpr int H = 2 * CAP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (idx >= count) return;
+  const int i = list[idx];
+  unsigned char* wbase = smem_raw + (size_t)warp * (24 * CAP);
+  double* vals = (double*)wbase;
+  int* keys = (int*)(wbase + 8 * CAP);
+  int* cols = (int*)(wbase + 16 * CAP);
+  unsigned short* slot = (unsigned short*)(wbase + 20 * CAP);
+  for (int k = lane; k < H; k += 32) keys[k] = EMPTY;
+  __syncwarp();
+  const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+  int cnt = 0;
+  bool over = false;
+  for (int64_t base = a0; base < a1 && !over; base += 32) {
+    const int64_t p = base + lane;
+    long long bs = 0, be = 0;
+    double av = 0.0;
+    if (p < a1) {
+      int j = __ldg(Acol + p);
+      av = __ldg(Aval + p);
+      bs = __ldg(Brp + j);
+      be = __ldg(Brp + j + 1);
+    }
+    const int nn = (int)min((int64_t)32, a1 - base);
+    for (int t = 0; t < nn && !over; ++t) {
+      const long long s = shfl64(bs, t), e = shfl64(be, t);
+      const double a = shfld(av, t);
+      for (long long q0 = s; q0 < e; q0 += 32) {
+        const long long q = q0 + lane;
+        const bool act = q < e;
+        int c = 0;
+        double prod = 0.0;
+        if (act) { c = __ldg(Bcol + q); prod = __dmul_rn(a, __ldg(Bval + q)); }
+        // (the table has 2 x CAP slots and at most CAP + 31 keys before the check below: never full)
+        unsigned h;
+        const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
+        const unsigned newmask = __ballot_sync(FULL, isnew);
+        if (cnt + __popc(newmask) > CAP) { over = true; break; }
+        if (isnew) {
+          const int sl = cnt + __popc(newmask & lanemask_lt());
+          slot[h] = (unsigned short)sl;
+          cols[sl] = c;
+          vals[sl] = prod;
+        } else if (act) {
+          const int sl = slot[h];
+          vals[sl] = __dadd_rn(vals[sl], prod);
+        }
+        cnt += __popc(newmask);
+        __syncwarp();
+      }
+    }
+  }
+  if (over) {
+    if (lane == 0) overflow_list[atomicAdd(overflow_count, 1)] = i;
+    return;
+  }
+  unsigned long long* sb = (unsigned long long*)keys;
+  int n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  for (int k = lane; k < n2; k += 32)
+    sb[k] = (k < cnt) ? (((unsigned long long)(unsigned)cols[k] << 32) | (unsigned)k) : ~0ull;
+  __syncwarp();
+  warp_bitonic_sort(sb, n2, lane);
+  const long long ob = arena_base + (long long)idx * CAP;
+  for (int k = lane; k < cnt; k += 32) {
+    const unsigned long long e = sb[k];
+    arena_col[ob + k] = (int)(e >> 32);
+    arena_val[ob + k] = vals[(unsigned)(e & 0xffffffffu)];
+  }
+  if (lane == 0) { arena_off[i] = ob; rownnz[i] = cnt; fused[i] = 1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1914,6 +2011,7 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_ROW_CHARGE")) t->row_charge = std::max(0LL, atoll(e));
   t->deterministic = flag("B200_DETERMINISTIC");
   if (const char* e = getenv("B200_ESC")) t->esc = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("B200_FUSE")) t->fuse = atoi(e) ? 1 : 0;
   if (t->deterministic) t->on_chip = true;
 }
 
@@ -2272,12 +2370,14 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   // warp-table bins; `Hopt`: optimistic table size tried first (0 = none), rows that overflow it
   // are collected on the device and retried in the full-size table without a host round trip
   int* d_over = nullptr;  // [0] overflow count per retry pass, then the lists
+  // `src_list` / `src_count`: the rows left over by an earlier pass (list and length on the device)
+  // instead of the whole bin
   auto launch_sym_warp = [&](int bin, auto kernel_full, int H, int WPB, auto kernel_opt, int Hopt,
-                             int slot) -> int {
+                             int slot, const int* src_list = nullptr, const int* src_count = nullptr) -> int {
     const int cntb = sb.cnt[bin];
     if (!cntb) return B200_OK;
-    const int* lst = sb.d_list + sb.off[bin];
-    tick(2 * bin);
+    const int* lst = src_list ? src_list : sb.d_list + sb.off[bin];
+    if (!src_list) tick(2 * bin);
     sym_timed[bin] = true;
     if (Hopt) {
       const int WO = 8;
@@ -2286,7 +2386,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       if (r) return r;
       int* ocount = d_over + slot;
       int* olist = d_over + 8 + (size_t)slot * m;
-      kernel_opt<<<(cntb + WO - 1) / WO, WO * 32, so, st>>>(lst, cntb, nullptr, row_lo, A.rowptr, A.col,
+      kernel_opt<<<(cntb + WO - 1) / WO, WO * 32, so, st>>>(lst, cntb, src_count, row_lo, A.rowptr, A.col,
                                                           B.rowptr, B.col, d_cnt, Hopt * 3 / 4 - 32,
                                                           olist, ocount);
       const size_t sf = (size_t)WPB * H * sizeof(int);
@@ -2300,7 +2400,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       const size_t smem = (size_t)WPB * H * sizeof(int);
       int r = set_smem(kernel_full, smem);
       if (r) return r;
-      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(lst, cntb, nullptr, row_lo, A.rowptr,
+      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(lst, cntb, src_count, row_lo, A.rowptr,
                                                                 A.col, B.rowptr, B.col, d_cnt, H,
                                                                 nullptr, nullptr);
       ++launches;
@@ -2309,18 +2409,18 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     return B200_OK;
   };
   if (sb.cnt[SB_W4K] || sb.cnt[SB_W16K]) {
-    B200_CUDA(T.alloc(&d_over, (size_t)8 + 2 * (size_t)std::max(m, 1)));
+    B200_CUDA(T.alloc(&d_over, (size_t)8 + 3 * (size_t)std::max(m, 1)));
     B200_CUDA(cudaMemsetAsync(d_over, 0, 8 * sizeof(int), st));
   }
-  if ((rc = launch_sym_warp(SB_W256, k_sym_warp<256>, 256, 8, k_sym_warp<256>, 0, 0))) return rc;
-  if ((rc = launch_sym_warp(SB_W1K, k_sym_warp<1024>, 1024, 8, k_sym_warp<1024>, 0, 0))) return rc;
-  if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8, k_sym_warp<1024>, 1024, 0))) return rc;
-  if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3, k_sym_warp<4096>, 4096, 1))) return rc;
 
-  // rows sorted on chip (esc.cuh), plain SpGEMM: computed HERE, once — the finished row waits in
-  // the arena, its length goes into the row counts like any symbolic result
+  // rows finished in the symbolic phase (plain SpGEMM): the finished row waits in the arena, its
+  // length goes into the row counts like any symbolic result.  Two kinds:
+  //  - rows sorted on chip (esc.cuh): arena slice = the row's products;
+  //  - SB_W4K rows tried as 128-entry numeric rows (k_num_warp_fused): arena slot = list position x 128,
+  //    after the slices of the first kind.
   int64_t* d_escoff = nullptr;
   int* d_escwork = nullptr;
+  unsigned char* d_fused = nullptr;
   int esc_col_bits = 1;
   while (esc_col_bits < 32 && (1ll << esc_col_bits) < (long long)n) ++esc_col_bits;
 #define LAUNCH_ESC(RM, LIST, COUNT, BTE, IPTE, SLOT, OFFS, ROUT, NNZ, TIMER)                    \
@@ -2336,26 +2436,39 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     ++launches;                                                                                 \
   }
   unsigned long long* d_esc = nullptr;  // [0] true unpruned entries of the rows sorted on chip
-  if (sb.cnt[SB_ESC2K] || sb.cnt[SB_ESC8K]) {
+  const bool esc_rows = sb.cnt[SB_ESC2K] || sb.cnt[SB_ESC8K];
+  if (esc_rows) {
     B200_CUDA(T.alloc(&d_esc, 2));
     B200_CUDA(cudaMemsetAsync(d_esc, 0, 2 * sizeof(unsigned long long), st));
     B200_CUDA(T.alloc(&d_escwork, 2));
     B200_CUDA(cudaMemsetAsync(d_escwork, 0, 2 * sizeof(int), st));
   }
-  if (mode == MODE_SPGEMM && (sb.cnt[SB_ESC2K] || sb.cnt[SB_ESC8K])) {
-    long long* d_len = nullptr;
-    B200_CUDA(T.alloc(&d_len, (size_t)m + 1));
-    B200_CUDA(T.alloc(&d_escoff, (size_t)m + 1));
-    k_esc_len<<<(m + 256) / 256, 256, 0, st>>>(d_bin, d_flops, m, d_len);
-    void* tmp = nullptr;
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_len, (long long*)d_escoff, m + 1, st);
-    B200_CUDA(T.alloc((char**)&tmp, tb ? tb : 1));
-    cub::DeviceScan::ExclusiveSum(tmp, tb, d_len, (long long*)d_escoff, m + 1, st);
+  bool fuse = mode == MODE_SPGEMM && c.tun.fuse != 0 && sb.cnt[SB_W4K] > 0;
+  if (fuse) {  // the slots must fit next to C itself: otherwise the ordinary two-pass path
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t slots = (size_t)sb.cnt[SB_W4K] * FUSED_CAP;
+    const size_t have = c.arena_cap >= slots ? slots : 0;   // already allocated: costs nothing
+    if ((slots - have) * 12 * 3 > free_b) fuse = false;     // slots + the rows again in C + head-room
+  }
+  if (mode == MODE_SPGEMM && (esc_rows || fuse)) {
     long long h_need = 0;
-    B200_CUDA(d2h_small(&h_need, d_escoff + m, sizeof(long long), st));
-    B200_CUDA(sync_fetch(st));
-    if ((rc = ensure_arena((size_t)h_need))) return rc;
+    B200_CUDA(T.alloc(&d_escoff, (size_t)m + 1));
+    if (esc_rows) {
+      long long* d_len = nullptr;
+      B200_CUDA(T.alloc(&d_len, (size_t)m + 1));
+      k_esc_len<<<(m + 256) / 256, 256, 0, st>>>(d_bin, d_flops, m, d_len);
+      void* tmp = nullptr;
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, d_len, (long long*)d_escoff, m + 1, st);
+      B200_CUDA(T.alloc((char**)&tmp, tb ? tb : 1));
+      cub::DeviceScan::ExclusiveSum(tmp, tb, d_len, (long long*)d_escoff, m + 1, st);
+      B200_CUDA(d2h_small(&h_need, d_escoff + m, sizeof(long long), st));
+      B200_CUDA(sync_fetch(st));
+      launches += 2;
+    }
+    const size_t fused_slots = fuse ? (size_t)sb.cnt[SB_W4K] * FUSED_CAP : 0;
+    if ((rc = ensure_arena((size_t)h_need + fused_slots))) return rc;
     RmclOut eo = {};
     eo.arena_col = c.arena_col;
     eo.arena_val = c.arena_val;
@@ -2363,8 +2476,28 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     sym_timed[SB_ESC8K] = sb.cnt[SB_ESC8K] > 0;
     LAUNCH_ESC(false, sb.d_list + sb.off[SB_ESC2K], sb.cnt[SB_ESC2K], 256, 8, 0, d_escoff, eo, d_cnt, 2 * SB_ESC2K)
     LAUNCH_ESC(false, sb.d_list + sb.off[SB_ESC8K], sb.cnt[SB_ESC8K], 512, 16, 1, d_escoff, eo, d_cnt, 2 * SB_ESC8K)
-    launches += 2;
+    if (fuse) {
+      const int cntb = sb.cnt[SB_W4K];
+      B200_CUDA(T.alloc(&d_fused, (size_t)m));
+      B200_CUDA(cudaMemsetAsync(d_fused, 0, (size_t)m, st));
+      const size_t smem = (size_t)8 * 24 * FUSED_CAP;
+      if ((rc = set_smem(k_num_warp_fused<FUSED_CAP>, smem))) return rc;
+      int* fcount = d_over + 2;
+      int* flist = d_over + 8 + 2 * (size_t)m;
+      tick(2 * SB_W4K);
+      k_num_warp_fused<FUSED_CAP><<<(cntb + 7) / 8, 256, smem, st>>>(
+          sb.d_list + sb.off[SB_W4K], cntb, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,
+          h_need, c.arena_col, c.arena_val, d_escoff, d_cnt, d_fused, flist, fcount);
+      ++launches;
+      // the rows with more than 128 columns: ordinary symbolic pass (and numeric pass later)
+      if ((rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8, k_sym_warp<1024>, 1024, 0, flist, fcount)))
+        return rc;
+    }
   }
+  if ((rc = launch_sym_warp(SB_W256, k_sym_warp<256>, 256, 8, k_sym_warp<256>, 0, 0))) return rc;
+  if ((rc = launch_sym_warp(SB_W1K, k_sym_warp<1024>, 1024, 8, k_sym_warp<1024>, 0, 0))) return rc;
+  if (!fuse && (rc = launch_sym_warp(SB_W4K, k_sym_warp<4096>, 4096, 8, k_sym_warp<1024>, 1024, 0))) return rc;
+  if ((rc = launch_sym_warp(SB_W16K, k_sym_warp<16384>, 16384, 3, k_sym_warp<4096>, 4096, 1))) return rc;
 
   // large rows: bitmap
   unsigned long long* d_bmstore = nullptr;  // stored bitmaps of the symbolic bitmap bin
@@ -2503,7 +2636,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   if (m > 0) {
     const long long light_p = c.tun.light_p >= 0 ? c.tun.light_p : 2560LL * std::max(1, nparts / 2);
     k_num_bins<<<(m + 255) / 256, 256, 0, st>>>(d_cnt, d_flops, m, num_big_from, light_p,
-                                                nparts > 2 ? light_p : 0, d_bin, A.rowptr, row_lo, d_nbin);
+                                                nparts > 2 ? light_p : 0, d_bin, A.rowptr, row_lo, d_fused, d_nbin);
     ++launches;
   }
   B200_CUDA(cudaMemsetAsync(d_cnt + m, 0, sizeof(int), st));
@@ -2590,7 +2723,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     return B200_OK;
   };
   if (mode == MODE_SPGEMM) {
-    for (int bin : {NB_ESC2K, NB_ESC8K})
+    for (int bin : {NB_ESC2K, NB_ESC8K, NB_FUSED})
       if (nb.cnt[bin]) {   // rows finished on chip during the symbolic phase: from the arena into C
         tick(32 + 2 * bin);
         k_esc_gather<<<(unsigned)(((long long)nb.cnt[bin] * 32 + 255) / 256), 256, 0, st>>>(

@@ -797,3 +797,30 @@ def test_rmcl_rows_sorted_on_chip(gpu, name, make, b200_options):
     Mt, _, hist = gpu.gpuRmclIter(6, A, A)
     ol.assert_same(M_of(Mt), want, TOL, name + " loop, rows sorted on chip")
     assert np.allclose(hist, hist_w, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,make", [("stencil27", lambda s: s.synth_stencil27(12, 11, 10)), SYNTH[0], SYNTH[2],
+                                       HEAVY[0]])
+def test_spgemm_rows_finished_in_the_symbolic_phase(gpu, name, make, b200_options):
+    """Plain SpGEMM rows of 512..2048 products are tried as 128-entry numeric rows while the
+    symbolic phase runs (k_num_warp_fused): those that fit are only copied into C afterwards,
+    the others take the ordinary symbolic + numeric passes.  A warp row accumulates in A-entry
+    order either way, so both settings give the same bits, and both match the checker."""
+    A = make(gpu)
+    dG = A.toGpuCSR()
+    b200_options(B200_FUSE=0)
+    dC0, st0 = gpu.gpuSpMMWrapper(dG, dG, want_stats=True)
+    two_pass = dC0.toCpuCSR()
+    dC0.deviceDispose()
+    b200_options(B200_FUSE=1)
+    dC1, st1 = gpu.gpuSpMMWrapper(dG, dG, want_stats=True)
+    fused = dC1.toCpuCSR()
+    dC1.deviceDispose(); dG.deviceDispose()
+    assert st0["bins_rows"][9] == 0
+    if name == "stencil27":
+        assert st1["bins_rows"][9] > 0 and st1["num_bin_nnzC"][9] > 0
+    assert st1["nnz_out"] == st0["nnz_out"]
+    assert np.array_equal(fused.rowPtr, two_pass.rowPtr) and np.array_equal(fused.colInd, two_pass.colInd)
+    # rows of the warp bins are bit-identical; heavy rows (global fp64 RED) to the tolerance
+    assert np.allclose(fused.values, two_pass.values, rtol=1e-12, atol=0)
+    ol.assert_same(M_of(fused), want_spgemm(A, A), TOL, name + " rows finished in the symbolic phase")
