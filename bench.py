@@ -389,9 +389,10 @@ def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
     def loop(dT):
         return smf.gpuRmclIterSharded(iters, dG, dT, want_counts=True)
 
+    warm_iter_ms = []
     for _ in range(warmup):
         dT = A.toGpuCSR()
-        loop(dT)
+        warm_iter_ms.append([round(float(x), 1) for x in loop(dT)[2]])
         dT.deviceDispose()
     dTs = [A.toGpuCSR() for _ in range(steps)]     # Mt0 of every timed loop: resident before the clock starts
     barrier()
@@ -399,11 +400,12 @@ def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches = 0
-    loops_ms = []
+    loops_ms, loops_iter_ms = [], []
     for dT in dTs:
         done, hist, ms_it, counts = loop(dT)
         launches += int(counts[:, 4].sum())
         loops_ms.append(round(float(ms_it.sum()), 3))
+        loops_iter_ms.append([round(float(x), 1) for x in ms_it])
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -431,6 +433,8 @@ def rmcl_measure(args, env, name, steps, warmup, want_cpu, want_e2e):
                 "traffic": None, "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
                 "loop_algorithmic_bytes": int(sum(bytes_it)),
                 "loops_ms_rank0": loops_ms,   # sum of the library's per-iteration CUDA-event times, per timed loop
+                "loops_iteration_ms_rank0": loops_iter_ms,
+                "warmup_loops_iteration_ms_rank0": warm_iter_ms,
                 "per_iteration": {"ms": [round(float(x), 3) for x in ms_it],
                                   "products": [int(x) for x in counts[:, 0]],
                                   "nnz_new_Mt": [int(x) for x in counts[:, 1]],

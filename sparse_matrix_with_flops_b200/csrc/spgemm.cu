@@ -362,37 +362,39 @@ k_sym_warp(const int* __restrict__ list, int count, const int* __restrict__ coun
   // handed to the next size up (overflow_list) only if it really has more than `limit` columns.
   extern __shared__ int smem_i[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
   if (count_dev) count = *count_dev;   // retry pass: the list length lives on the device
-  if (idx >= count) return;
-  const int i = list[idx];
   int* keys = smem_i + warp * H;
-  for (int k = lane; k < H; k += 32) keys[k] = EMPTY;
-  __syncwarp();
-  const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
-  int cnt = 0;  // warp-uniform
-  bool over = false;
-  for (int64_t base = a0; base < a1 && !over; base += 32) {
-    const int64_t p = base + lane;
-    long long bs = 0, be = 0;
-    if (p < a1) { int j = __ldg(Acol + p); bs = __ldg(Brp + j); be = __ldg(Brp + j + 1); }
-    const int nn = (int)min((int64_t)32, a1 - base);
-    for (int t = 0; t < nn && !over; ++t) {
-      const long long s = shfl64(bs, t), e = shfl64(be, t);
-      for (long long q0 = s; q0 < e; q0 += 32) {
-        const long long q = q0 + lane;
-        const bool act = q < e;
-        const int c = act ? __ldg(Bcol + q) : 0;
-        unsigned h;
-        const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
-        cnt += __popc(__ballot_sync(FULL, isnew));
-        if (cnt > limit) { over = true; break; }   // the next step could fill the table
+  // (grid-stride: a retry pass is launched with a capped grid, its list is usually short)
+  for (int idx = blockIdx.x * (blockDim.x >> 5) + warp; idx < count; idx += gridDim.x * (blockDim.x >> 5)) {
+    const int i = list[idx];
+    __syncwarp();
+    for (int k = lane; k < H; k += 32) keys[k] = EMPTY;
+    __syncwarp();
+    const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
+    int cnt = 0;  // warp-uniform
+    bool over = false;
+    for (int64_t base = a0; base < a1 && !over; base += 32) {
+      const int64_t p = base + lane;
+      long long bs = 0, be = 0;
+      if (p < a1) { int j = __ldg(Acol + p); bs = __ldg(Brp + j); be = __ldg(Brp + j + 1); }
+      const int nn = (int)min((int64_t)32, a1 - base);
+      for (int t = 0; t < nn && !over; ++t) {
+        const long long s = shfl64(bs, t), e = shfl64(be, t);
+        for (long long q0 = s; q0 < e; q0 += 32) {
+          const long long q = q0 + lane;
+          const bool act = q < e;
+          const int c = act ? __ldg(Bcol + q) : 0;
+          unsigned h;
+          const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
+          cnt += __popc(__ballot_sync(FULL, isnew));
+          if (cnt > limit) { over = true; break; }   // the next step could fill the table
+        }
       }
     }
-  }
-  if (lane == 0) {
-    if (over) overflow_list[atomicAdd(overflow_count, 1)] = i;
-    else rownnz[i] = cnt;
+    if (lane == 0) {
+      if (over) overflow_list[atomicAdd(overflow_count, 1)] = i;
+      else rownnz[i] = cnt;
+    }
   }
 }
 
@@ -607,13 +609,54 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
 }
 
 
-// k_num_warp<CAP, false> run OPTIMISTICALLY in the symbolic phase (plain SpGEMM): for rows whose
+// The numeric row built OPTIMISTICALLY in the symbolic phase (plain SpGEMM): for rows whose
 // products would need one of the large tables but whose columns may well fit the smallest ones —
-// every interior row of a 27-point stencil has 729 products and 125 columns — the numeric row is
-// built at once in a CAP-entry table.  If it fits, the sorted row waits in a fixed arena slot
-// (list position x CAP) for C's row offsets, its length goes into the row counts, and the row
-// needs neither a symbolic pass nor a second numeric one; if not, the row is handed to the
+// every interior row of a 27-point stencil has 729 products and 125 columns — the row is
+// accumulated at once in a 128-entry table.  If it fits, the sorted row waits in a fixed arena
+// slot (list position x 128) for C's row offsets, its length goes into the row counts, and the
+// row needs neither a symbolic pass nor a second numeric one; if not, the row is handed to the
 // regular two-pass path (overflow_list).
+//
+// A leaner loop than k_num_warp's (which keeps first-touch order for the rMCL epilogue): the
+// value sits AT the key's hash slot (no slot indirection), a new key is claimed with one
+// shared-memory CAS, the (col, val) loads of the next step are issued before the current step is
+// accumulated, and the row is sorted in registers (4 columns per lane, shuffles) with the values
+// looked up by column afterwards.  Every entry still receives its products in ascending A-entry
+// order with separately rounded multiply and add: the same bits as k_num_warp and the reference.
+// shared memory per warp (28 * CAP bytes): vals fp64[2 CAP] | keys int[2 CAP] | cols int[CAP]
+__device__ __forceinline__ void cmpex_u32(unsigned& a, unsigned& b, bool up) {
+  const unsigned lo = min(a, b), hi = max(a, b);
+  a = up ? lo : hi;
+  b = up ? hi : lo;
+}
+// bitonic sort of 128 keys held 4 per lane: element e = 4 * lane + r, ascending
+__device__ __forceinline__ void warp_sort128_regs(unsigned (&key)[4], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 128; k <<= 1) {
+    // direction of the length-k run element e belongs to: bit log2(k) of e (k = 128: ascending)
+    const bool up = (k >= 4) ? ((lane & (k >> 2)) == 0) : true;
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 4) {
+        const bool lower = (lane & (j >> 2)) == 0;
+        const bool keepmin = lower == up;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const unsigned other = __shfl_xor_sync(FULL, key[r], j >> 2);
+          key[r] = keepmin ? min(key[r], other) : max(key[r], other);
+        }
+      } else if (j == 2) {
+        // k >= 4 here; (r, r + 2) pairs
+        cmpex_u32(key[0], key[2], up);
+        cmpex_u32(key[1], key[3], up);
+      } else {  // j == 1: (0,1) and (2,3); for k == 2 the direction is bit 1 of e, i.e. of r
+        cmpex_u32(key[0], key[1], k == 2 ? true : up);
+        cmpex_u32(key[2], key[3], k == 2 ? false : up);
+      }
+    }
+  }
+}
+
 template <int CAP>
 __global__ void __launch_bounds__(256)
 k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
@@ -624,77 +667,114 @@ k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
                  int64_t* __restrict__ arena_off, int* __restrict__ rownnz,
                  unsigned char* __restrict__ fused, int* __restrict__ overflow_list,
                  int* __restrict__ overflow_count) {
+  static_assert(CAP == 128, "the register sort holds 4 x 32 columns");
   constexpr int H = 2 * CAP;
+  constexpr unsigned mask = H - 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
   if (idx >= count) return;
   const int i = list[idx];
-  unsigned char* wbase = smem_raw + (size_t)warp * (24 * CAP);
+  unsigned char* wbase = smem_raw + (size_t)warp * (28 * CAP);
   double* vals = (double*)wbase;
-  int* keys = (int*)(wbase + 8 * CAP);
-  int* cols = (int*)(wbase + 16 * CAP);
-  unsigned short* slot = (unsigned short*)(wbase + 20 * CAP);
-  for (int k = lane; k < H; k += 32) keys[k] = EMPTY;
+  int* keys = (int*)(wbase + 16 * CAP);
+  int* cols = (int*)(wbase + 24 * CAP);
+#pragma unroll
+  for (int k = 0; k < H / 32; ++k) keys[k * 32 + lane] = EMPTY;
   __syncwarp();
   const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
   int cnt = 0;
   bool over = false;
-  for (int64_t base = a0; base < a1 && !over; base += 32) {
-    const int64_t p = base + lane;
-    long long bs = 0, be = 0;
+  for (int64_t abase = a0; abase < a1 && !over; abase += 32) {
+    const int64_t p = abase + lane;
+    long long bs = 0;
+    int bl = 0;
     double av = 0.0;
     if (p < a1) {
-      int j = __ldg(Acol + p);
+      const int j = __ldg(Acol + p);
       av = __ldg(Aval + p);
       bs = __ldg(Brp + j);
-      be = __ldg(Brp + j + 1);
+      bl = (int)(__ldg(Brp + j + 1) - bs);
     }
-    const int nn = (int)min((int64_t)32, a1 - base);
-    for (int t = 0; t < nn && !over; ++t) {
-      const long long s = shfl64(bs, t), e = shfl64(be, t);
-      const double a = shfld(av, t);
-      for (long long q0 = s; q0 < e; q0 += 32) {
-        const long long q = q0 + lane;
-        const bool act = q < e;
-        int c = 0;
-        double prod = 0.0;
-        if (act) { c = __ldg(Bcol + q); prod = __dmul_rn(a, __ldg(Bval + q)); }
-        // (the table has 2 x CAP slots and at most CAP + 31 keys before the check below: never full)
-        unsigned h;
-        const bool isnew = warp_find_or_insert<H>(keys, c, act, h);
-        const unsigned newmask = __ballot_sync(FULL, isnew);
-        if (cnt + __popc(newmask) > CAP) { over = true; break; }
-        if (isnew) {
-          const int sl = cnt + __popc(newmask & lanemask_lt());
-          slot[h] = (unsigned short)sl;
-          cols[sl] = c;
-          vals[sl] = prod;
-        } else if (act) {
-          const int sl = slot[h];
-          vals[sl] = __dadd_rn(vals[sl], prod);
-        }
-        cnt += __popc(newmask);
-        __syncwarp();
+    const int nn = (int)min((int64_t)32, a1 - abase);
+    // a step = 32 consecutive entries of one B row; the loads of step n + 1 are in flight while
+    // step n is accumulated
+    int t = 0, o0 = 0;
+    long long s = shfl64(bs, 0);
+    int len = __shfl_sync(FULL, bl, 0);
+    double a = shfld(av, 0);
+    bool act = lane < len;
+    int c = 0;
+    double v = 0.0;
+    if (act) { c = __ldg(Bcol + s + lane); v = __ldg(Bval + s + lane); }
+    while (true) {
+      int nt = t, no0 = o0 + 32;
+      if (no0 >= len) { ++nt; no0 = 0; }
+      const bool more = nt < nn;   // warp-uniform
+      long long s2 = s;
+      int len2 = len, c2 = 0;
+      double a2 = a, v2 = 0.0;
+      bool act2 = false;
+      if (more) {
+        s2 = shfl64(bs, nt);
+        len2 = __shfl_sync(FULL, bl, nt);
+        a2 = shfld(av, nt);
+        act2 = no0 + lane < len2;
+        if (act2) { c2 = __ldg(Bcol + s2 + no0 + lane); v2 = __ldg(Bval + s2 + no0 + lane); }
       }
+      // ---- the current step: find or claim the slot of c (the keys of a step are pairwise
+      // distinct, so a lane can lose a slot only to a different key), then accumulate there
+      const double prod = __dmul_rn(a, v);
+      unsigned h = hash_col<H>(c);
+      bool done = !act, isnew = false;
+      while (true) {
+        if (!done) {
+          const int k = keys[h];
+          if (k == c) done = true;
+          else if (k == EMPTY && atomicCAS(&keys[h], EMPTY, c) == EMPTY) { done = true; isnew = true; }
+          else h = (h + 1) & mask;
+        }
+        if (__all_sync(FULL, done)) break;
+      }
+      const unsigned newmask = __ballot_sync(FULL, isnew);
+      const int nnew = __popc(newmask);
+      // (2 CAP slots and at most CAP + 31 keys when this check fires: the table is never full)
+      if (cnt + nnew > CAP) { over = true; break; }
+      if (isnew) {
+        vals[h] = prod;
+        cols[cnt + __popc(newmask & lanemask_lt())] = c;
+      } else if (act) {
+        vals[h] = __dadd_rn(vals[h], prod);
+      }
+      cnt += nnew;
+      __syncwarp();
+      if (!more) break;
+      t = nt; o0 = no0; s = s2; len = len2; a = a2; act = act2; c = c2; v = v2;
     }
   }
   if (over) {
     if (lane == 0) overflow_list[atomicAdd(overflow_count, 1)] = i;
     return;
   }
-  unsigned long long* sb = (unsigned long long*)keys;
-  int n2 = 1;
-  while (n2 < cnt) n2 <<= 1;
-  for (int k = lane; k < n2; k += 32)
-    sb[k] = (k < cnt) ? (((unsigned long long)(unsigned)cols[k] << 32) | (unsigned)k) : ~0ull;
-  __syncwarp();
-  warp_bitonic_sort(sb, n2, lane);
+  // ---- ascending columns: sort in registers, look the values up by column
+  unsigned key[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = 4 * lane + r;
+    key[r] = (e < cnt) ? (unsigned)cols[e] : 0xffffffffu;   // (columns are < 2^31: the pad sorts last)
+  }
+  warp_sort128_regs(key, lane);
   const long long ob = arena_base + (long long)idx * CAP;
-  for (int k = lane; k < cnt; k += 32) {
-    const unsigned long long e = sb[k];
-    arena_col[ob + k] = (int)(e >> 32);
-    arena_val[ob + k] = vals[(unsigned)(e & 0xffffffffu)];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = 4 * lane + r;
+    if (e < cnt) {
+      const int cc = (int)key[r];
+      unsigned h = hash_col<H>(cc);
+      while (keys[h] != cc) h = (h + 1) & mask;
+      arena_col[ob + e] = cc;
+      arena_val[ob + e] = vals[h];
+    }
   }
   if (lane == 0) { arena_off[i] = ob; rownnz[i] = cnt; fused[i] = 1; }
 }
@@ -2311,6 +2391,8 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
         }
       }
       c.arena_cap = got;
+      if (c.tun.prof)
+        fprintf(stderr, "[b200 prof] arena: %zu -> %zu entries (asked %zu)\n", old_cap, got, (size_t)unpruned);
     }
     return B200_OK;
   };
@@ -2386,13 +2468,15 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       if (r) return r;
       int* ocount = d_over + slot;
       int* olist = d_over + 8 + (size_t)slot * m;
-      kernel_opt<<<(cntb + WO - 1) / WO, WO * 32, so, st>>>(lst, cntb, src_count, row_lo, A.rowptr, A.col,
+      // (passes that work on a device-side list: a grid that covers the machine, rows by stride)
+      const int retry_grid = c.sm_count * 8;
+      kernel_opt<<<src_list ? std::min((cntb + WO - 1) / WO, retry_grid) : (cntb + WO - 1) / WO, WO * 32, so, st>>>(
+                                                          lst, cntb, src_count, row_lo, A.rowptr, A.col,
                                                           B.rowptr, B.col, d_cnt, Hopt * 3 / 4 - 32,
                                                           olist, ocount);
       const size_t sf = (size_t)WPB * H * sizeof(int);
       if ((r = set_smem(kernel_full, sf))) return r;
-      // grid sized for the worst case; warps beyond the overflow count exit at once
-      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, sf, st>>>(olist, cntb, ocount, row_lo, A.rowptr,
+      kernel_full<<<std::min((cntb + WPB - 1) / WPB, retry_grid), WPB * 32, sf, st>>>(olist, cntb, ocount, row_lo, A.rowptr,
                                                               A.col, B.rowptr, B.col, d_cnt, H,
                                                               olist, ocount);
       launches += 2;
@@ -2400,7 +2484,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       const size_t smem = (size_t)WPB * H * sizeof(int);
       int r = set_smem(kernel_full, smem);
       if (r) return r;
-      kernel_full<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(lst, cntb, src_count, row_lo, A.rowptr,
+      kernel_full<<<src_list ? std::min((cntb + WPB - 1) / WPB, c.sm_count * 8) : (cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(lst, cntb, src_count, row_lo, A.rowptr,
                                                                 A.col, B.rowptr, B.col, d_cnt, H,
                                                                 nullptr, nullptr);
       ++launches;
@@ -2480,7 +2564,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       const int cntb = sb.cnt[SB_W4K];
       B200_CUDA(T.alloc(&d_fused, (size_t)m));
       B200_CUDA(cudaMemsetAsync(d_fused, 0, (size_t)m, st));
-      const size_t smem = (size_t)8 * 24 * FUSED_CAP;
+      const size_t smem = (size_t)8 * 28 * FUSED_CAP;
       if ((rc = set_smem(k_num_warp_fused<FUSED_CAP>, smem))) return rc;
       int* fcount = d_over + 2;
       int* flist = d_over + 8 + 2 * (size_t)m;
