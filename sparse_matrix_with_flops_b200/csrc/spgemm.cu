@@ -657,7 +657,8 @@ __device__ __forceinline__ void warp_sort128_regs(unsigned (&key)[4], int lane) 
   }
 }
 
-template <int CAP>
+// IDX32: B has fewer than 2^31 entries — its row offsets travel between lanes in one register
+template <int CAP, bool IDX32>
 __global__ void __launch_bounds__(256)
 k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
                  const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
@@ -670,6 +671,7 @@ k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
   static_assert(CAP == 128, "the register sort holds 4 x 32 columns");
   constexpr int H = 2 * CAP;
   constexpr unsigned mask = H - 1;
+  using idx_t = typename std::conditional<IDX32, unsigned, unsigned long long>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -685,71 +687,94 @@ k_num_warp_fused(const int* __restrict__ list, int count, int row_lo,
   const int64_t a0 = Arp[row_lo + i], a1 = Arp[row_lo + i + 1];
   int cnt = 0;
   bool over = false;
+
+  // a step = 32 consecutive entries of one B row
+  struct Step { idx_t s; int t, o0, len, c; double a, v; };
+  idx_t bs = 0;
+  int bl = 0;
+  double av = 0.0;
+  auto fetch = [&](Step& n, int t, int o0) {   // issue the (col, val) loads of step (t, o0)
+    n.t = t;
+    n.o0 = o0;
+    if (IDX32) n.s = (idx_t)__shfl_sync(FULL, (unsigned)bs, t);
+    else n.s = (idx_t)shfl64((long long)bs, t);
+    n.len = __shfl_sync(FULL, bl, t);
+    n.a = shfld(av, t);
+    n.c = -1;   // -1 (EMPTY is never a column): this lane has no product in the step
+    n.v = 0.0;
+    if (o0 + lane < n.len) {
+      const idx_t q = n.s + (idx_t)(o0 + lane);
+      n.c = __ldg(Bcol + q);
+      n.v = __ldg(Bval + q);
+    }
+  };
+  // find or claim the slot of the step's column (the columns of a step are pairwise distinct, so
+  // a lane can lose a slot only to a different column), accumulate there; false: row overflows
+  auto process = [&](const Step& st) -> bool {
+    const int c = st.c;
+    const bool act = c >= 0;
+    const double prod = __dmul_rn(st.a, st.v);
+    unsigned h = hash_col<H>(c);
+    int k = act ? keys[h] : c;
+    int state = (k == c) ? 1 : 0;   // 0 pending, 1 present (or no product), 2 claimed now
+    if (!__all_sync(FULL, state != 0)) {
+      while (true) {
+        if (state == 0) {
+          if (k == EMPTY && atomicCAS(&keys[h], EMPTY, c) == EMPTY) {
+            state = 2;
+          } else {
+            h = (h + 1) & mask;
+            k = keys[h];
+            if (k == c) state = 1;
+          }
+        }
+        if (__all_sync(FULL, state != 0)) break;
+      }
+      const unsigned newmask = __ballot_sync(FULL, state == 2);
+      const int nnew = __popc(newmask);
+      // (2 CAP slots, at most CAP + 31 columns when this fires: the table is never full)
+      if (cnt + nnew > CAP) return false;
+      if (state == 2) {
+        vals[h] = prod;
+        cols[cnt + __popc(newmask & lanemask_lt())] = c;
+      }
+      cnt += nnew;
+    }
+    if (state == 1 && act) vals[h] = __dadd_rn(vals[h], prod);
+    __syncwarp();
+    return true;
+  };
+
   for (int64_t abase = a0; abase < a1 && !over; abase += 32) {
     const int64_t p = abase + lane;
-    long long bs = 0;
-    int bl = 0;
-    double av = 0.0;
+    bs = 0;
+    bl = 0;
+    av = 0.0;
     if (p < a1) {
       const int j = __ldg(Acol + p);
       av = __ldg(Aval + p);
-      bs = __ldg(Brp + j);
-      bl = (int)(__ldg(Brp + j + 1) - bs);
+      const long long b0 = __ldg(Brp + j);
+      bs = (idx_t)b0;
+      bl = (int)(__ldg(Brp + j + 1) - b0);
     }
     const int nn = (int)min((int64_t)32, a1 - abase);
-    // a step = 32 consecutive entries of one B row; the loads of step n + 1 are in flight while
-    // step n is accumulated
-    int t = 0, o0 = 0;
-    long long s = shfl64(bs, 0);
-    int len = __shfl_sync(FULL, bl, 0);
-    double a = shfld(av, 0);
-    bool act = lane < len;
-    int c = 0;
-    double v = 0.0;
-    if (act) { c = __ldg(Bcol + s + lane); v = __ldg(Bval + s + lane); }
+    // two step records used alternately: the loads of the next step are in flight while the
+    // current one is accumulated, and no register moves between them
+    Step A, B;
+    fetch(A, 0, 0);
     while (true) {
-      int nt = t, no0 = o0 + 32;
-      if (no0 >= len) { ++nt; no0 = 0; }
-      const bool more = nt < nn;   // warp-uniform
-      long long s2 = s;
-      int len2 = len, c2 = 0;
-      double a2 = a, v2 = 0.0;
-      bool act2 = false;
-      if (more) {
-        s2 = shfl64(bs, nt);
-        len2 = __shfl_sync(FULL, bl, nt);
-        a2 = shfld(av, nt);
-        act2 = no0 + lane < len2;
-        if (act2) { c2 = __ldg(Bcol + s2 + no0 + lane); v2 = __ldg(Bval + s2 + no0 + lane); }
-      }
-      // ---- the current step: find or claim the slot of c (the keys of a step are pairwise
-      // distinct, so a lane can lose a slot only to a different key), then accumulate there
-      const double prod = __dmul_rn(a, v);
-      unsigned h = hash_col<H>(c);
-      bool done = !act, isnew = false;
-      while (true) {
-        if (!done) {
-          const int k = keys[h];
-          if (k == c) done = true;
-          else if (k == EMPTY && atomicCAS(&keys[h], EMPTY, c) == EMPTY) { done = true; isnew = true; }
-          else h = (h + 1) & mask;
-        }
-        if (__all_sync(FULL, done)) break;
-      }
-      const unsigned newmask = __ballot_sync(FULL, isnew);
-      const int nnew = __popc(newmask);
-      // (2 CAP slots and at most CAP + 31 keys when this check fires: the table is never full)
-      if (cnt + nnew > CAP) { over = true; break; }
-      if (isnew) {
-        vals[h] = prod;
-        cols[cnt + __popc(newmask & lanemask_lt())] = c;
-      } else if (act) {
-        vals[h] = __dadd_rn(vals[h], prod);
-      }
-      cnt += nnew;
-      __syncwarp();
-      if (!more) break;
-      t = nt; o0 = no0; s = s2; len = len2; a = a2; act = act2; c = c2; v = v2;
+      int nt = A.t, no = A.o0 + 32;
+      if (no >= A.len) { ++nt; no = 0; }
+      const bool moreB = nt < nn;
+      if (moreB) fetch(B, nt, no);
+      if (!process(A)) { over = true; break; }
+      if (!moreB) break;
+      nt = B.t; no = B.o0 + 32;
+      if (no >= B.len) { ++nt; no = 0; }
+      const bool moreA = nt < nn;
+      if (moreA) fetch(A, nt, no);
+      if (!process(B)) { over = true; break; }
+      if (!moreA) break;
     }
   }
   if (over) {
@@ -2529,11 +2554,12 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
   bool fuse = mode == MODE_SPGEMM && c.tun.fuse != 0 && sb.cnt[SB_W4K] > 0;
   if (fuse) {  // the slots must fit next to C itself: otherwise the ordinary two-pass path
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
     const size_t slots = (size_t)sb.cnt[SB_W4K] * FUSED_CAP;
-    const size_t have = c.arena_cap >= slots ? slots : 0;   // already allocated: costs nothing
-    if ((slots - have) * 12 * 3 > free_b) fuse = false;     // slots + the rows again in C + head-room
+    if (c.arena_cap < slots) {   // (an arena that already holds them costs nothing)
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (slots * 12 * 3 > free_b) fuse = false;     // slots + the rows again in C + head-room
+    }
   }
   if (mode == MODE_SPGEMM && (esc_rows || fuse)) {
     long long h_need = 0;
@@ -2565,11 +2591,13 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(T.alloc(&d_fused, (size_t)m));
       B200_CUDA(cudaMemsetAsync(d_fused, 0, (size_t)m, st));
       const size_t smem = (size_t)8 * 28 * FUSED_CAP;
-      if ((rc = set_smem(k_num_warp_fused<FUSED_CAP>, smem))) return rc;
+      const bool idx32 = B.nnz < (1LL << 31);
+      if ((rc = idx32 ? set_smem(k_num_warp_fused<FUSED_CAP, true>, smem)
+                      : set_smem(k_num_warp_fused<FUSED_CAP, false>, smem))) return rc;
       int* fcount = d_over + 2;
       int* flist = d_over + 8 + 2 * (size_t)m;
       tick(2 * SB_W4K);
-      k_num_warp_fused<FUSED_CAP><<<(cntb + 7) / 8, 256, smem, st>>>(
+      (idx32 ? k_num_warp_fused<FUSED_CAP, true> : k_num_warp_fused<FUSED_CAP, false>)<<<(cntb + 7) / 8, 256, smem, st>>>(
           sb.d_list + sb.off[SB_W4K], cntb, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,
           h_need, c.arena_col, c.arena_val, d_escoff, d_cnt, d_fused, flist, fcount);
       ++launches;
