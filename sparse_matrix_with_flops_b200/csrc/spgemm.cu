@@ -3084,6 +3084,9 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
     stats->ms_symbolic = t12;
     stats->ms_numeric = t34;
     stats->ms_other = t23 + t45;
+    if (c.tun.prof)
+      fprintf(stderr, "[b200 prof] rows %d..%d: flops %.2f symbolic %.2f bins+offsets %.2f numeric %.2f compaction %.2f ms\n",
+              row_lo, row_hi, t01, t12, t23, t34, t45);
     stats->products = h_tot[1];
     stats->nnz_out = nnz_out;
     // (rows sorted on chip reserved their products as a bound: report what they really held)
