@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <chrono>
 #include <vector>
 #include "b200_spgemm.h"
 
@@ -131,7 +132,13 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
 template <typename T>
 inline cudaError_t dalloc(T** p, size_t count) {
   if (count == 0) count = 1;
-  return cudaMallocAsync((void**)p, count * sizeof(T), ctx().stream);
+  if (!ctx().tun.prof) return cudaMallocAsync((void**)p, count * sizeof(T), ctx().stream);
+  // B200_PROF: report allocations that stall the host (the pool had to get memory from the driver)
+  const auto t0 = std::chrono::steady_clock::now();
+  const cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx().stream);
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (ms > 1.0) fprintf(stderr, "[b200 prof] cudaMallocAsync of %.1f MB took %.1f ms\n", count * sizeof(T) / 1e6, ms);
+  return e;
 }
 template <typename T>
 inline void dfree(T* p) {

@@ -128,6 +128,22 @@ static long long arena_budget_entries() {
     if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
+    // Give the pool its working set in ONE piece before the arena takes its share.  The step's
+    // temporaries and row blocks (a few GB) are then carved from this block; without it the pool
+    // grows in driver calls in the middle of the loop — 8 ms each as a rule, but one
+    // cudaMallocAsync of 110 MB was measured at 702 ms next to a 53 GB arena (R-MAT scale 20,
+    // B200_PROF=1), 11 % of the whole loop.  (The pool keeps what it gets: release threshold = max.)
+    {
+      const size_t reserve = std::min<size_t>(free_b / 10, (size_t)16 << 30);
+      void* p = nullptr;
+      if (reserve > 0 && cudaMallocAsync(&p, reserve, c.stream) == cudaSuccess) {
+        cudaFreeAsync(p, c.stream);
+        cudaStreamSynchronize(c.stream);
+        free_b -= reserve;
+      } else {
+        cudaGetLastError();
+      }
+    }
     // 40 % of what is free now plus what the arena already holds; the operands, the result and
     // the pipeline's scratch need the rest
     c.arena_budget = (long long)(0.40 * (double)(free_b + c.arena_cap * 12)) / 12;
