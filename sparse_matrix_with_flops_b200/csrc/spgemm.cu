@@ -459,20 +459,13 @@ __device__ __forceinline__ void topk_cut(Count count, double thresh, double rmax
 //   cols  int[CAP]       slot -> column           \ later reused together as fp64[CAP]:
 //   slot  ushort[2*CAP]  hash slot -> output slot / squared values in sorted order
 template <int CAP, bool RMCL>
-__global__ void __launch_bounds__(256)
-k_num_warp(const int* __restrict__ list, int count, int row_lo,
+__device__ __forceinline__ void num_warp_row(int i, unsigned char* wbase, int lane, int row_lo,
            const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
            const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
            const int* __restrict__ Bcol, const double* __restrict__ Bval,
            const int64_t* __restrict__ Crp, int* __restrict__ Ccol, double* __restrict__ Cval,
-           RmclOut ro) {
+           const RmclOut& ro) {
   constexpr int H = 2 * CAP;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (idx >= count) return;
-  const int i = list[idx];
-  unsigned char* wbase = smem_raw + (size_t)warp * (24 * CAP);
   double* vals = (double*)wbase;
   int* keys = (int*)(wbase + 8 * CAP);
   int* cols = (int*)(wbase + 16 * CAP);
@@ -608,6 +601,36 @@ k_num_warp(const int* __restrict__ list, int count, int row_lo,
   }
 }
 
+
+// `work_counter` != nullptr: the warps draw rows from a shared counter instead of owning one
+// row each — with the large tables one 8-warp block fills an SM, and a block of statically
+// assigned rows lasts as long as its heaviest row.
+template <int CAP, bool RMCL>
+__global__ void __launch_bounds__(256)
+k_num_warp(const int* __restrict__ list, int count, int row_lo,
+           const int64_t* __restrict__ Arp, const int* __restrict__ Acol,
+           const double* __restrict__ Aval, const int64_t* __restrict__ Brp,
+           const int* __restrict__ Bcol, const double* __restrict__ Bval,
+           const int64_t* __restrict__ Crp, int* __restrict__ Ccol, double* __restrict__ Cval,
+           RmclOut ro, int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wbase = smem_raw + (size_t)warp * (24 * CAP);
+  if (!work_counter) {
+    const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (idx < count)
+      num_warp_row<CAP, RMCL>(list[idx], wbase, lane, row_lo, Arp, Acol, Aval, Brp, Bcol, Bval, Crp, Ccol, Cval, ro);
+    return;
+  }
+  while (true) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(work_counter, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+    if (idx >= count) break;
+    num_warp_row<CAP, RMCL>(list[idx], wbase, lane, row_lo, Arp, Acol, Aval, Brp, Bcol, Bval, Crp, Ccol, Cval, ro);
+    __syncwarp();   // the next row re-uses the tables
+  }
+}
 
 // The numeric row built OPTIMISTICALLY in the symbolic phase (plain SpGEMM): for rows whose
 // products would need one of the large tables but whose columns may well fit the smallest ones —
@@ -2819,16 +2842,23 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
   }
 
   // ---- 5. numeric per bin
+  int* d_wnum = nullptr;   // row counters of the dynamically scheduled warp-table kernels
+  B200_CUDA(T.alloc(&d_wnum, 2));
+  B200_CUDA(cudaMemsetAsync(d_wnum, 0, 2 * sizeof(int), st));
   auto launch_num_warp = [&](int bin, auto kernel, int CAP, int WPB) -> int {
     const int cntb = nb.cnt[bin];
     if (!cntb) return B200_OK;
     const size_t smem = (size_t)WPB * 24 * CAP;
     int r = set_smem(kernel, smem);
     if (r) return r;
+    // (large tables: one or two blocks per SM — a grid that covers the machine, rows drawn dynamically)
+    const bool dynamic = CAP >= 1024;
+    const int per_sm = std::max(1, (int)((c.smem_optin + 1024) / (smem + 1024)));
+    const int grid = dynamic ? std::min((cntb + WPB - 1) / WPB, per_sm * c.sm_count) : (cntb + WPB - 1) / WPB;
     tick(32 + 2 * bin);
-    kernel<<<(cntb + WPB - 1) / WPB, WPB * 32, smem, st>>>(
+    kernel<<<grid, WPB * 32, smem, st>>>(
         nb.d_list + nb.off[bin], cntb, row_lo, A.rowptr, A.col, A.val, B.rowptr, B.col, B.val,
-        d_urp, C->col, C->val, ro);
+        d_urp, C->col, C->val, ro, dynamic ? d_wnum + (CAP >= 2048 ? 1 : 0) : nullptr);
     tick(32 + 2 * bin + 1);
     num_timed[bin] = true;
     ++launches;
