@@ -102,6 +102,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="development: skip the CPU baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-pin", action="store_true",
+                    help="e2e leg: plain malloc result blocks (the library's default) instead of the "
+                         "page-locked block cache (b200_host_cache_pin)")
     ap.add_argument("--row-charge", type=int, default=32768,
                     help="products-equivalent fixed cost of a heavy row in the N>1 row partition")
     return ap.parse_args()
@@ -559,6 +562,14 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local)
+    # host block cache of the e2e leg: large enough to hold one step's result blocks of this rank
+    # (the library's own default is min(RAM / 4, 64 GB) per process; read once, at first use)
+    if "B200_HOST_CACHE_GB" not in os.environ:
+        try:
+            kb = int(next(l for l in open("/proc/meminfo") if l.startswith("MemTotal")).split()[1])
+            os.environ["B200_HOST_CACHE_GB"] = "%.1f" % (min(0.5 * kb / 2**20, 160.0) / world)
+        except Exception:  # noqa: BLE001
+            pass
     if world > 1:
         # (NCCL prints its version banner on stdout when the first communicator is created)
         with quiet_stdout():
@@ -816,6 +827,10 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
            if world == 1 else
            "b200_csr_upload + b200_spgemm_device_rows + b200_csr_download_rows per row block (host malloc'd int CSR in/out)")
 
+    # Result blocks come back through b200_host_free; with the page-locked cache the blocks of the
+    # warm-up step are registered once and every later download is one DMA into them.
+    pin = not args.no_pin
+    lib.b200_host_cache_pin(1 if pin else 0)
     # A rank whose call fails still takes part in every collective below (no deadlock); the leg
     # is then reported as failed instead of taking the whole bench line down.
     err = None
@@ -833,6 +848,13 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
                 err = repr(e)
     barrier()
     sec = (time.perf_counter() - t0) / args.e2e_steps
+    hits, miss, direct, pinned = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int()
+    lib.b200_host_cache_stats(C.byref(hits), C.byref(miss), C.byref(direct), C.byref(pinned))
+    cache = {"mode": "page-locked blocks (b200_host_cache_pin)" if pin else "malloc blocks (default)",
+             "limit_gb": os.environ.get("B200_HOST_CACHE_GB"), "hits": hits.value, "misses": miss.value,
+             "direct_downloads": direct.value, "page_locked_blocks_rank0": pinned.value}
+    lib.b200_host_cache_drop()     # un-registers: the legs that follow get the host memory back
+    lib.b200_host_cache_pin(0)
     import torch
     import torch.distributed as dist
     t = torch.tensor([sec, 1.0 if err else 0.0], dtype=torch.float64, device="cuda")
@@ -845,7 +867,7 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
     sec = float(t[0])
     return {"value": 2.0 * P / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0]),
             "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
-            "warmup": 1, "row_blocks": nblk,
+            "warmup": 1, "row_blocks": nblk, "host_block_cache": cache,
             "api": api + ", wall clock incl. H2D + D2H"}
 
 

@@ -254,6 +254,15 @@ void b200_host_free(void* p);
 int b200_host_cache_info(long long* bytes, int* blocks, long long* limit_bytes);
 /* Gives every kept block back to the OS (b200_finalize does the same). */
 int b200_host_cache_drop(void);
+/* on != 0: blocks that enter the cache are page-locked (cudaHostRegister, once) and stay so while
+ * they circulate; a later download into such a block is one DMA, without the staging buffer and
+ * the host copy of the default path (B200_HOST_PIN=1 in the environment does the same).  In this
+ * mode every block the library returned MUST be released with b200_host_free(); free() on a
+ * page-locked block is an error.  Default: off (plain malloc blocks, free() legal). */
+int b200_host_cache_pin(int on);
+/* Counters since the process started: large-block requests served from the cache / not served,
+ * downloads that went straight into a page-locked block, and page-locked blocks alive now. */
+int b200_host_cache_stats(long long* hits, long long* misses, long long* direct, int* pinned_blocks);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,8 @@ SIGNATURES = {
     "b200_host_free": (None, [C.c_void_p]),
     "b200_host_cache_info": (C.c_int, [c_ll_p, c_int_p, c_ll_p]),
     "b200_host_cache_drop": (C.c_int, []),
+    "b200_host_cache_pin": (C.c_int, [C.c_int]),
+    "b200_host_cache_stats": (C.c_int, [c_ll_p, c_ll_p, c_ll_p, c_int_p]),
 }
 
 # harness-only generators: libb200synth.so (include/b200_synth.h), host code

@@ -135,6 +135,9 @@ void parallel_copy(void* dst, const void* src, size_t bytes, int spare = 0) {
   }
 }
 
+// true if [dst, dst + bytes) lies inside a page-locked block of the host cache (defined below)
+bool host_block_is_pinned(const void* dst, size_t bytes);
+
 // device -> host block.  ordered == true: everything queued on the library stream before the
 // call is waited for.  ordered == false (download worker): only the copy stream is touched; the
 // submitting thread has already made the copy stream wait for the producer.
@@ -152,6 +155,13 @@ int d2h_staged(void* dst, const void* src, size_t bytes, bool ordered = true) {
     if (rc) return rc;
     B200_CUDA(cudaEventRecord(c.xfer_ev, c.stream));
     B200_CUDA(cudaStreamWaitEvent(c.copy_stream, c.xfer_ev, 0));
+  }
+  if (host_block_is_pinned(dst, bytes)) {
+    // a block of the page-locked cache (b200_host_cache_pin): one DMA straight into it, no
+    // staging buffer and no host copy
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.copy_stream));
+    B200_CUDA(cudaStreamSynchronize(c.copy_stream));
+    return B200_OK;
   }
   const size_t nchunks = (bytes + PIN_BYTES - 1) / PIN_BYTES;
   for (size_t k = 0; k <= nchunks; ++k) {
@@ -202,13 +212,57 @@ int h2d_staged(void* dst, const void* src, size_t bytes) {
 // free() lets the library keep them (still malloc blocks, their capacity read back with
 // malloc_usable_size) for the next download, up to B200_HOST_CACHE_GB (default: a quarter of the
 // physical memory, at most 64 GB; 0 turns the cache off).
+//
+// Opt-in (b200_host_cache_pin(1) or B200_HOST_PIN=1): a block that enters the cache is
+// page-locked (cudaHostRegister, once) and stays so while it circulates, so later downloads DMA
+// straight into it — no pinned staging buffer, no host copy; with several ranks on one host the
+// staging copies are what bounds the download (two host threads per rank at 8 ranks).  The price
+// is the contract: in this mode blocks MUST come back through b200_host_free(), never free().
 struct HostCache {
   std::mutex mu;
   std::vector<std::pair<size_t, void*>> blocks;   // (capacity, pointer)
+  std::vector<std::pair<char*, size_t>> pinned;   // page-locked blocks, kept or handed out
   size_t total = 0, limit = 0;
-  long hits = 0, misses = 0;
+  long hits = 0, misses = 0, direct = 0;
   bool limit_known = false;
+  int pin = -1;                                    // -1: read B200_HOST_PIN on first use
   static constexpr size_t BIG = (size_t)64 << 20;
+
+  bool pin_mode() {
+    if (pin < 0) { const char* e = getenv("B200_HOST_PIN"); pin = (e && atoi(e) != 0) ? 1 : 0; }
+    return pin > 0;
+  }
+  // (mu held)
+  int find_pinned(const void* p) const {
+    for (int i = 0; i < (int)pinned.size(); ++i) if ((const void*)pinned[i].first == p) return i;
+    return -1;
+  }
+  void unpin_locked(void* p) {
+    const int i = find_pinned(p);
+    if (i < 0) return;
+    if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    pinned.erase(pinned.begin() + i);
+  }
+  void pin_locked(void* p, size_t cap) {
+    if (!pin_mode() || find_pinned(p) >= 0 || !ctx().ready) return;
+    cudaSetDevice(ctx().device);
+    if (cudaHostRegister(p, cap, cudaHostRegisterPortable) == cudaSuccess)
+      pinned.push_back(std::make_pair((char*)p, cap));
+    else
+      cudaGetLastError();   // (locked-memory limit, ...): the block stays an ordinary one
+  }
+  bool covers(const void* dst, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    const char* d = (const char*)dst;
+    for (auto& b : pinned)
+      if (d >= b.first && d + bytes <= b.first + b.second) { ++direct; return true; }
+    return false;
+  }
+  // a block that leaves the library's custody for good
+  void release(void* p) {
+    { std::lock_guard<std::mutex> lk(mu); unpin_locked(p); }
+    free(p);
+  }
 
   size_t cap_limit() {
     if (!limit_known) {
@@ -249,22 +303,25 @@ struct HostCache {
       for (int i = 1; i < (int)blocks.size(); ++i) if (blocks[i].first < blocks[s].first) s = i;
       if (blocks[s].first >= cap) return false;            // everything kept is at least as useful
       total -= blocks[s].first;
+      unpin_locked(blocks[s].second);
       free(blocks[s].second);
       blocks.erase(blocks.begin() + s);
     }
     if (total + cap > limit) return false;
     blocks.push_back(std::make_pair(cap, p));
     total += cap;
+    pin_locked(p, cap);
     return true;
   }
   void drop_all() {
     std::lock_guard<std::mutex> lk(mu);
-    for (auto& b : blocks) free(b.second);
+    for (auto& b : blocks) { unpin_locked(b.second); free(b.second); }
     blocks.clear();
     total = 0;
   }
 };
 HostCache& host_cache() { static HostCache* h = new HostCache; return *h; }
+bool host_block_is_pinned(const void* dst, size_t bytes) { return host_cache().covers(dst, bytes); }
 
 void* host_block_alloc(size_t bytes) {
   void* p = host_cache().take(bytes);
@@ -279,7 +336,12 @@ void* host_block_alloc(size_t bytes) {
 struct HostBlock {
   int* I = nullptr; int* J = nullptr; double* V = nullptr;
   int64_t begin = 0, cnt = 0;
-  void drop() { free(I); free(J); free(V); I = nullptr; J = nullptr; V = nullptr; }
+  void drop() {   // (J and V may be blocks of the cache, possibly page-locked: never plain free())
+    free(I);
+    for (void* p : {(void*)J, (void*)V})
+      if (p && !host_cache().give(p)) host_cache().release(p);
+    I = nullptr; J = nullptr; V = nullptr;
+  }
 };
 
 // allocate the host block and bring the (rebased, 32-bit) row offsets over; library stream
@@ -440,7 +502,24 @@ extern "C" {
 const char* b200_last_error(void) { return g_err.c_str(); }
 
 void b200_host_free(void* p) {
-  if (p && !host_cache().give(p)) free(p);
+  if (p && !host_cache().give(p)) host_cache().release(p);
+}
+
+int b200_host_cache_stats(long long* hits, long long* misses, long long* direct, int* pinned_blocks) {
+  HostCache& h = host_cache();
+  std::lock_guard<std::mutex> lk(h.mu);
+  if (hits) *hits = h.hits;
+  if (misses) *misses = h.misses;
+  if (direct) *direct = h.direct;
+  if (pinned_blocks) *pinned_blocks = (int)h.pinned.size();
+  return B200_OK;
+}
+
+int b200_host_cache_pin(int on) {
+  HostCache& h = host_cache();
+  std::lock_guard<std::mutex> lk(h.mu);
+  h.pin = on ? 1 : 0;
+  return B200_OK;
 }
 
 int b200_host_cache_info(long long* bytes, int* blocks, long long* limit_bytes) {

@@ -74,8 +74,8 @@ lib.b200_host_cache_drop()
 out.append(info())
 print(out)
 """ % ROOT
-    def run(gb):
-        env = dict(os.environ, B200_HOST_CACHE_GB=gb)
+    def run(gb, pin="0"):
+        env = dict(os.environ, B200_HOST_CACHE_GB=gb, B200_HOST_PIN=pin)
         r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env, timeout=120)
         assert r.returncode == 0, r.stderr
         return eval(r.stdout.strip())
@@ -87,6 +87,8 @@ print(out)
     assert a[4][:2] == (0, 0) and abs(a[4][2] - 0.2 * (1 << 30)) < 2
     z = run("0")
     assert all(x[:2] == (0, 0) for x in z)
+    # page-locked mode without a device context: blocks are kept as ordinary ones
+    assert run("0.2", pin="1") == a
 
 
 def test_product_does_not_touch_the_oracle():

@@ -824,3 +824,52 @@ def test_spgemm_rows_finished_in_the_symbolic_phase(gpu, name, make, b200_option
     # rows of the warp bins are bit-identical; heavy rows (global fp64 RED) to the tolerance
     assert np.allclose(fused.values, two_pass.values, rtol=1e-12, atol=0)
     ol.assert_same(M_of(fused), want_spgemm(A, A), TOL, name + " rows finished in the symbolic phase")
+
+
+def test_page_locked_block_cache(gpu):
+    """b200_host_cache_pin(1): blocks released through b200_host_free are page-locked once and the
+    next download lands in them with one DMA (no staging copy).  Same bytes as the default path;
+    eviction, drop and a block that is not kept all unregister before the memory is freed."""
+    import ctypes as C
+    from sparse_matrix_with_flops_b200 import _lib
+    lib = _lib.load()
+    ip, dp = _lib.c_int_p, _lib.c_double_p
+    A = gpu.synth_rmat(14, 16, 5, False)
+    dA = A.toGpuCSR()
+    dC = gpu.gpuSpMMWrapper(dA, dA)
+    want = dC.toCpuCSR()
+    assert want.nnz * 8 >= (64 << 20), "blocks below 64 MB are not cached"
+
+    def download():
+        IC, JC, Cv, nnz = ip(), ip(), dp(), C.c_int(0)
+        _lib.check(lib.b200_csr_download_rows(dC.handle, 0, A.rows, C.byref(IC), C.byref(JC), C.byref(Cv),
+                                              C.byref(nnz)))
+        n = nnz.value
+        got = (np.ctypeslib.as_array(IC, (A.rows + 1,)).copy(), np.ctypeslib.as_array(JC, (n,)).copy(),
+               np.ctypeslib.as_array(Cv, (n,)).copy())
+        for p in (IC, JC, Cv):
+            lib.b200_host_free(C.cast(p, C.c_void_p))
+        return got
+
+    lib.b200_host_cache_drop()
+    assert lib.b200_host_cache_pin(1) == 0
+    try:
+        first = download()      # fresh blocks: staged; released -> kept and page-locked
+        second = download()     # the same blocks again: direct DMA
+        third = download()
+        for got in (first, second, third):
+            assert np.array_equal(got[0], want.rowPtr) and np.array_equal(got[1], want.colInd)
+            assert np.array_equal(got[2], want.values)
+        b, n, l = C.c_longlong(), C.c_int(), C.c_longlong()
+        lib.b200_host_cache_info(C.byref(b), C.byref(n), C.byref(l))
+        assert n.value >= 1 and b.value >= want.nnz * 8
+        hits, miss, direct, pinned = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int()
+        lib.b200_host_cache_stats(C.byref(hits), C.byref(miss), C.byref(direct), C.byref(pinned))
+        assert pinned.value >= 2 and direct.value >= 4, (hits.value, miss.value, direct.value, pinned.value)
+    finally:
+        lib.b200_host_cache_drop()
+        lib.b200_host_cache_pin(0)
+    plain = download()
+    assert np.array_equal(plain[2], want.values)
+    lib.b200_host_cache_drop()
+    dC.deviceDispose(); dA.deviceDispose()
