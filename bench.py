@@ -102,6 +102,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="development: skip the CPU baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-api", default="auto", choices=["auto", "streamed", "sequential"],
+                    help="e2e leg: b200_spgemm_csr_stream (download of block b overlaps the product of block "
+                         "b+1) or upload / product / download per row block; auto = streamed on one GPU, "
+                         "sequential with several ranks on one host")
     ap.add_argument("--no-pin", action="store_true",
                     help="e2e leg: plain malloc result blocks (the library's default) instead of the "
                          "page-locked block cache (b200_host_cache_pin)")
@@ -822,9 +826,10 @@ def run_e2e(args, smf, lib, A, rank, world, barrier, lo, hi, P):
             sink(None, r0, r1, IC, JC, Cv, nnzC.value)
         dA.deviceDispose()
 
-    one = one_streamed if world == 1 else one_sequential
+    streamed = world == 1 if args.e2e_api == "auto" else args.e2e_api == "streamed"
+    one = one_streamed if streamed else one_sequential
     api = ("b200_spgemm_csr_stream (host int CSR in, malloc'd host int CSR row blocks out through a callback)"
-           if world == 1 else
+           if streamed else
            "b200_csr_upload + b200_spgemm_device_rows + b200_csr_download_rows per row block (host malloc'd int CSR in/out)")
 
     # Result blocks come back through b200_host_free; with the page-locked cache the blocks of the
