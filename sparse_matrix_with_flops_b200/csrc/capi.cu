@@ -240,6 +240,7 @@ struct HostCache {
   void unpin_locked(void* p) {
     const int i = find_pinned(p);
     if (i < 0) return;
+    if (ctx().ready) cudaSetDevice(ctx().device);   // (never create a context on another device)
     if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
     pinned.erase(pinned.begin() + i);
   }
