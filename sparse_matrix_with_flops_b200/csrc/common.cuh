@@ -46,6 +46,7 @@ struct Tunables {
                              // always; default (-1): in matrices wider than two column parts (> 1 M columns)
   int fuse = -1;             // B200_FUSE=0/1: plain SpGEMM rows of 512..2048 products are first tried as 128-entry
                              // numeric rows in the symbolic phase (k_num_warp_fused) never / always; default: always
+                             // (2: always, with the 64-bit B offsets of operands beyond 2^31 entries — testing)
   bool prof = false;         // B200_PROF: per-phase diagnostics on stderr
   int l2[5] = {2, 1, 0, 1, 0};  // B200_L2POL=acc,ocol,bgather,bmstore,demote (L2Prio values)
   long long sym_big_from = -1;  // B200_SYM_BIG_FROM, B200_NUM_BIG_FROM, B200_LIGHT_P: bin cuts (-1: default)

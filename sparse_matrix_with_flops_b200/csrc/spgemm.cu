@@ -2166,7 +2166,7 @@ void load_tunables(Tunables* t) {
   if (const char* e = getenv("B200_ROW_CHARGE")) t->row_charge = std::max(0LL, atoll(e));
   t->deterministic = flag("B200_DETERMINISTIC");
   if (const char* e = getenv("B200_ESC")) t->esc = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("B200_FUSE")) t->fuse = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("B200_FUSE")) t->fuse = atoi(e);   // 0 off, 1 on, 2 on with 64-bit B offsets (testing)
   if (t->deterministic) t->on_chip = true;
 }
 
@@ -2641,7 +2641,7 @@ int run_pipeline(const DevCSR& A, const DevCSR& B, int row_lo, int row_hi, Mode 
       B200_CUDA(T.alloc(&d_fused, (size_t)m));
       B200_CUDA(cudaMemsetAsync(d_fused, 0, (size_t)m, st));
       const size_t smem = (size_t)8 * 28 * FUSED_CAP;
-      const bool idx32 = B.nnz < (1LL << 31);
+      const bool idx32 = B.nnz < (1LL << 31) && c.tun.fuse != 2;
       if ((rc = idx32 ? set_smem(k_num_warp_fused<FUSED_CAP, true>, smem)
                       : set_smem(k_num_warp_fused<FUSED_CAP, false>, smem))) return rc;
       int* fcount = d_over + 2;

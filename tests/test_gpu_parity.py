@@ -815,7 +815,14 @@ def test_spgemm_rows_finished_in_the_symbolic_phase(gpu, name, make, b200_option
     b200_options(B200_FUSE=1)
     dC1, st1 = gpu.gpuSpMMWrapper(dG, dG, want_stats=True)
     fused = dC1.toCpuCSR()
-    dC1.deviceDispose(); dG.deviceDispose()
+    dC1.deviceDispose()
+    b200_options(B200_FUSE=2)   # the instance for operands with more than 2^31 entries (64-bit offsets)
+    dC2, st2 = gpu.gpuSpMMWrapper(dG, dG, want_stats=True)
+    wide = dC2.toCpuCSR()
+    dC2.deviceDispose(); dG.deviceDispose()
+    assert st2["bins_rows"][9] == st1["bins_rows"][9]
+    assert np.array_equal(wide.rowPtr, fused.rowPtr) and np.array_equal(wide.colInd, fused.colInd)
+    assert np.allclose(wide.values, fused.values, rtol=1e-12, atol=0)
     assert st0["bins_rows"][9] == 0
     if name == "stencil27":
         assert st1["bins_rows"][9] > 0 and st1["num_bin_nnzC"][9] > 0
